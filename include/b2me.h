@@ -1,0 +1,225 @@
+/*
+ * b2me.h — C-ABI of libb2me.so: the B200 (sm_100a) back end behind the MinkowskiEngine-compatible
+ * Python package and the batched pose pipeline of this repo.
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller owns every buffer (inputs, outputs, hash tables, workspaces); the library never
+ *     allocates, frees or synchronises; every entry point enqueues on the caller's stream;
+ *   - return value 0 = success, negative B2ME_E* otherwise (b2me_strerror gives the text);
+ *   - data-dependent counts (number of voxels V, ...) are written to device scalars; the caller reads
+ *     them back when it needs a host-side shape.
+ *
+ * Each entry point cites the reference interface it replaces (file:line in
+ * bcsefercik/markerless-robot-camera-calibration, or the third-party call made there).
+ */
+#ifndef B2ME_H_
+#define B2ME_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2me_stream_t; /* cudaStream_t */
+
+/* error codes */
+#define B2ME_OK 0
+#define B2ME_EINVAL (-1)   /* bad argument */
+#define B2ME_EWORKSPACE (-2) /* workspace / table too small */
+#define B2ME_ELAUNCH (-3)  /* CUDA launch error (cudaGetLastError) */
+#define B2ME_EUNSUPPORTED (-4) /* shape/dtype combination not built */
+
+/* dtypes */
+#define B2ME_F32 0
+#define B2ME_BF16 1
+
+/* activations fused in epilogues */
+#define B2ME_ACT_NONE 0
+#define B2ME_ACT_RELU 1
+#define B2ME_ACT_LEAKY 2
+
+int b2me_version(void);
+const char* b2me_strerror(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coordinate hashing (K1-K3).  A "table" is an open-addressing hash of 16-byte slots
+ * {uint64 key, uint32 val, pad}; key packs (batch:10 | x:18 | y:18 | z:18, biased), val = voxel row.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* slots needed for n keys (power of two >= 2n) and the byte size of such a table */
+int64_t b2me_table_slots(int64_t n);
+size_t b2me_table_bytes(int64_t n);
+/* scratch needed by b2me_quantize_unique / b2me_stride_map for n input rows with C feature channels */
+size_t b2me_unique_workspace_bytes(int64_t n, int C);
+
+/*
+ * K1 voxelise: replaces ME.TensorField(...).sparse() (app/inference_engine.py:405-415,
+ * test_segmentation.py:62-70) and ME.SparseTensor(...)/ME.utils.sparse_quantize coordinate handling
+ * (data/alivev2.py:290-296).
+ *   coords_f  [N,4] f32 (b,x,y,z), already multiplied by `scale` by the caller; floorf() is applied here;
+ *             OR coords_i [N,4] i32 (exactly one of the two non-null).
+ *   feats     [N,C] f32 (may be null when C == 0)
+ *   mode      0 = first point of each voxel wins (ME RANDOM_SUBSAMPLE / sparse_quantize),
+ *             1 = UNWEIGHTED_AVERAGE (exact fixed-point sum)
+ *   out_coords[N,4] i32 capacity, rows 0..V-1 valid, FIRST-OCCURRENCE order
+ *   out_feats [N,C] f32 capacity
+ *   inverse   [N] i32  point -> voxel row
+ *   first_idx [N] i32 capacity: voxel row -> index of its first point (may be null)
+ *   counts    [2] i32: counts[0] = V, counts[1] = error flag (non-zero: coordinate out of key range)
+ *   table     caller-owned, b2me_table_bytes(N); on return maps key -> voxel row (kept for K3)
+ */
+int b2me_quantize_unique(const float* coords_f, const int32_t* coords_i, int64_t N,
+                         const float* feats, int C, int mode,
+                         int32_t* out_coords, float* out_feats, int32_t* inverse, int32_t* first_idx,
+                         int32_t* counts, void* table, size_t table_bytes,
+                         void* ws, size_t ws_bytes, b2me_stream_t stream);
+
+/* per-voxel label for sparse_quantize(labels=..., ignore_label=...): the common label of the member
+ * points, ignore_label when they disagree (data/alivev2.py:290-296). labels [N] i32 -> out [V] i32 */
+int b2me_quantize_labels(const int32_t* labels, const int32_t* inverse, const int32_t* first_idx,
+                         int64_t N, int64_t V, int32_t ignore_label, int32_t* out_labels,
+                         b2me_stream_t stream);
+
+/*
+ * K2 stride map: output coordinates of a stride-2 MinkowskiConvolution (model/backbone/minkunet.py:60-82):
+ * unique(floor(c / ts_out) * ts_out) in first-occurrence order.
+ *   in_coords [V_in,4] i32 at tensor stride ts_out/2;  out_coords [V_in,4] capacity
+ *   in2out [V_in] i32 parent row; koff [V_in] u8 child offset index (x fastest, 0..7)
+ *   counts [2] i32 (V_out, error flag); table_out: b2me_table_bytes(V_in)
+ */
+int b2me_stride_map(const int32_t* in_coords, int64_t V_in, int ts_out,
+                    int32_t* out_coords, int32_t* in2out, uint8_t* koff, int32_t* counts,
+                    void* table_out, size_t table_bytes, void* ws, size_t ws_bytes,
+                    b2me_stream_t stream);
+
+/* kernel maps of the k=2,s=2 convolution and of its transpose from (in2out, koff):
+ *   nbr_down [V_out,8] i32: fine row feeding coarse row o at offset k, or -1   (MinkowskiConvolution k2 s2)
+ *   nbr_up   [V_in,8]  i32: coarse row feeding fine row f at offset k, or -1   (MinkowskiConvolutionTranspose,
+ *                            model/backbone/minkunet.py:87-109: exactly one valid entry per row) */
+int b2me_stride_kernel_maps(const int32_t* in2out, const uint8_t* koff, int64_t V_in, int64_t V_out,
+                            int32_t* nbr_down, int32_t* nbr_up, b2me_stream_t stream);
+
+/*
+ * K3 kernel map of a k=3, stride-1 convolution at tensor stride ts (every BasicBlock conv and the stem):
+ *   nbr [V,27] i32, offset index = (dx+1) + 3(dy+1) + 9(dz+1), entry = row of voxel c + d*ts, or -1.
+ *   tile_mask [ceil(V/128)] u32 (may be null): bit k set when any row of the 128-row tile has neighbour k.
+ */
+int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* table, size_t table_bytes,
+                       int32_t* nbr, uint32_t* tile_mask, b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse convolution (K4) = gather - GEMM - (no scatter: output-stationary), replaces
+ * ME.MinkowskiConvolution / MinkowskiConvolutionTranspose / MinkowskiLinear forward
+ * (model/backbone/minkunet.py:126-181, model/robotnet_segmentation.py:43-49) with the following
+ * MinkowskiBatchNorm (eval), residual add, ME.cat of two sources and ReLU/LeakyReLU folded in:
+ *     out[o, :] = act( (sum_k [in1|in2][nbr[o,k], :] @ W[k]) * scale + shift + residual[o, :] )
+ * nbr == NULL means identity map (K must be 1).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fp32-accumulate SIMT path; in/out/residual may be f32 or bf16; W is the module parameter
+ * [K, Cin1+Cin2, Cout] f32 */
+int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, int Cin2, int in_dtype,
+                         const float* W, const int32_t* nbr, int K, int64_t V_out, int Cout,
+                         const float* scale, const float* shift,
+                         const void* residual, int res_dtype, int act, float slope,
+                         void* out, int out_dtype, b2me_stream_t stream);
+
+/* tcgen05 path: bf16 operands, fp32 accumulation in TMEM.  Weights must be pre-packed. */
+size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout);
+int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout);
+int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, void* packed,
+                         b2me_stream_t stream);
+int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2,
+                       const void* packed_w, const int32_t* nbr, const uint32_t* tile_mask, int K,
+                       int64_t V_out, int Cout, const float* scale, const float* shift,
+                       const void* residual, int act, float slope,
+                       void* out, int out_dtype, b2me_stream_t stream);
+
+/* stand-alone per-channel affine + residual + activation (BatchNorm/ReLU that could not be folded) */
+int b2me_affine_act(const void* in, int in_dtype, int64_t V, int C, const float* scale,
+                    const float* shift, const void* residual, int res_dtype, int act, float slope,
+                    void* out, int out_dtype, b2me_stream_t stream);
+
+/* dtype conversion f32 <-> bf16 of n elements */
+int b2me_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Heads (K5, K6, K8)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* small-N linear: out[V,Cout] f32 = in[V,Cin] @ Wt^T + bias, Wt [Cout,Cin] f32 (nn.Linear layout),
+ * Cout <= 16; optional per-row argmax (lowest index wins ties, torch semantics of utils/output.py:67-73) */
+int b2me_linear_small(const void* in, int in_dtype, int64_t V, int Cin, const float* Wt,
+                      const float* bias, int Cout, float* out_logits, uint8_t* out_argmax,
+                      b2me_stream_t stream);
+
+/* SparseTensor.slice (app/inference_engine.py:417): out[i,:] = in[inverse[i],:] (f32 or bf16 rows) */
+int b2me_gather_rows(const void* in, int dtype, int C, const int32_t* index, int64_t N, void* out,
+                     b2me_stream_t stream);
+/* per-point labels straight from voxel labels (slice + argmax fused): out[i] = lab[inverse[i]] */
+int b2me_gather_labels(const uint8_t* voxel_labels, const int32_t* inverse, int64_t N,
+                       uint8_t* out, b2me_stream_t stream);
+
+/* K6: MinkowskiGlobalAvgPooling / MinkowskiGlobalMaxPooling (model/robotnet_encode.py:41,102;
+ * model/robotnet.py:43): per batch index reduce over voxel rows. coords [V,4] i32 (col 0 = batch),
+ * out [B,C] f32. mode 0 = mean, 1 = max. Deterministic. */
+int b2me_global_pool(const void* in, int dtype, const int32_t* coords, int64_t V, int C, int B,
+                     int mode, float* out, b2me_stream_t stream);
+
+/* K8a: get_key_point_predictions (utils/output.py:81-87), batched over segments.
+ * logits [n,K] f32, seg_offsets [S+1] i32 rows of each segment; for every (segment, class):
+ * best_prob = max_i softmax(logits[i])[class], best_idx = lowest such i (global row index). */
+int b2me_keypoint_reduce(const float* logits, int K, const int32_t* seg_offsets, int S,
+                         float* best_prob, int32_t* best_idx, b2me_stream_t stream);
+
+/* K8b: get_pred_center (utils/output.py:45-64): mean coordinate of the `topk` rows with the largest
+ * logits[:,col] in every segment (ties: lowest index first). out_center [S,3] f32 */
+int b2me_vote_center(const float* logits, int K, int col, const float* points_xyz,
+                     const int32_t* seg_offsets, int S, int topk, float* out_center,
+                     b2me_stream_t stream);
+
+/* predict_translation "magic" (app/inference_engine.py:459-489): per segment, p' = R(q)^T p,
+ * o = (max+min)/2, pos = R ([-0.015, 0, min_z(p'-o)] + o).  quat [S,4] wxyz f32, out [S,3] f32 */
+int b2me_translation_magic(const float* points_xyz, const int32_t* seg_offsets, int S,
+                           const float* quat_wxyz, float x_offset, double* out_pos,
+                           b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7: ClusterUtil.get_largest_cluster (utils/output.py:13-28; sklearn single linkage, 0.06 m) batched:
+ * connected components of the graph {d(i,j) < dist} inside every segment; mask[i] = 1 for the points
+ * of the largest component of their segment (ties: the component holding the lowest point index).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2me_cluster_workspace_bytes(int64_t n, int S);
+int b2me_largest_cluster(const float* points_xyz, const int32_t* seg_offsets, int S, int64_t n,
+                         double dist, uint8_t* out_mask, int32_t* out_sizes /* [S] largest size */,
+                         void* ws, size_t ws_bytes, b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9: get_rigid_transform_3D (utils/transformation.py:178-222) batched. ref/tgt [P,kmax,3] f64,
+ * npairs [P] i32 (<= kmax). out_R [P,9] f64 row-major, out_t [P,3] f64.
+ * ---------------------------------------------------------------------------------------------- */
+int b2me_kabsch_batched(const double* ref, const double* tgt, const int32_t* npairs, int P, int kmax,
+                        double* out_R, double* out_t, b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10: Open3D registration_icp(source=CAD, target=EE, max_corr, init, PointToPoint) as used by
+ * utils/icp.py:50-81, batched over frames. One CTA per frame; exact nearest neighbour within
+ * max_corr through a uniform grid over the frame's target points.
+ *   source_xyz [S,3] f32 (shared CAD cloud); target_xyz [T_total,3] f32, tgt_offsets [F+1] i32
+ *   init_T [F,16] f64 row-major 4x4; out_T [F,16] f64; out_stats [F,4] f64 = fitness, inlier_rmse,
+ *   iterations run, #correspondences
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2me_icp_workspace_bytes(int64_t T_total, int F);
+int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
+                         const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
+                         double max_corr, int max_iter, double rel_fitness, double rel_rmse,
+                         double* out_T, double* out_stats, void* ws, size_t ws_bytes,
+                         b2me_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ME_H_ */

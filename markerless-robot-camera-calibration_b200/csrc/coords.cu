@@ -1,0 +1,447 @@
+// coords.cu — K1 voxelise / unique, K2 stride map, K3 kernel maps (sm_100a).
+//
+// All three are HBM-bound integer kernels: one thread per point / voxel / (voxel, offset), coalesced
+// streaming reads and writes, random 16-byte sector accesses into an open-addressing hash table.
+// Determinism: the voxel that owns a key is the LOWEST point index that maps to it (atomicMin), and a
+// voxel's row is the exclusive prefix sum of the "I am the first point of my voxel" flags in point
+// order, so rows come out in first-occurrence order without a sort.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ scan
+#define SCAN_THREADS 512
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+size_t scan_ws_bytes(int64_t n) {
+    int64_t nb = ceil_div64(n > 0 ? n : 1, SCAN_TILE);
+    return align_up((size_t)(nb + 1) * sizeof(int32_t), 256);
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem /*>=32*/) {
+    // returns exclusive prefix of v over the block; *total = block sum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < (blockDim.x >> 5)) ? smem[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    int res = inc - v + smem[warp];
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int32_t* __restrict__ data, int64_t n,
+                                                              int32_t* __restrict__ block_sums) {
+    __shared__ int sm[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j)
+        if (base + j < n) s += data[base + j];
+    int total;
+    block_exclusive_scan(s, &total, sm);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_block_sums(int32_t* __restrict__ block_sums, int64_t nb,
+                                                         int32_t* __restrict__ total_out) {
+    __shared__ int sm[33];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += blockDim.x) {
+        int64_t i = base + threadIdx.x;
+        int v = (i < nb) ? block_sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total, sm);
+        int carry = carry_s;
+        if (i < nb) block_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int32_t* __restrict__ data, int64_t n,
+                                                             const int32_t* __restrict__ block_sums) {
+    __shared__ int sm[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        v[j] = (base + j < n) ? data[base + j] : 0;
+        s += v[j];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, &total, sm) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (base + j < n) data[base + j] = ex;
+        ex += v[j];
+    }
+}
+
+int exclusive_scan_i32(int32_t* data, int64_t n, int32_t* total, void* ws, cudaStream_t s) {
+    if (n <= 0) {
+        cudaMemsetAsync(total, 0, sizeof(int32_t), s);
+        return B2ME_OK;
+    }
+    int32_t* block_sums = reinterpret_cast<int32_t*>(ws);
+    const int64_t nb = ceil_div64(n, SCAN_TILE);
+    k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(data, n, block_sums);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, total);
+    k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(data, n, block_sums);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+__global__ void k_quantize_float(const float4* __restrict__ coords, int64_t n, int4* __restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = __ldg(coords + i);
+    // the caller has already multiplied by `scale` in fp32 (app/inference_engine.py:408); ME only floors
+    q[i] = make_int4((int)c.x, (int)floorf(c.y), (int)floorf(c.z), (int)floorf(c.w));
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+__global__ void k_quantize_stride(const int4* __restrict__ in, int64_t n, int ts_out, int4* __restrict__ q,
+                                  uint8_t* __restrict__ koff) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = __ldg(in + i);
+    const int ts_in = ts_out >> 1;
+    const int px = floor_div(c.y, ts_out) * ts_out;
+    const int py = floor_div(c.z, ts_out) * ts_out;
+    const int pz = floor_div(c.w, ts_out) * ts_out;
+    q[i] = make_int4(c.x, px, py, pz);
+    const int dx = (c.y - px) / ts_in, dy = (c.z - py) / ts_in, dz = (c.w - pz) / ts_in;
+    koff[i] = (uint8_t)(dx + 2 * dy + 4 * dz);  // x fastest
+}
+
+__global__ void k_hash_insert(const int4* __restrict__ q, int64_t n, HashSlot* __restrict__ tab,
+                              unsigned long long mask, int32_t* __restrict__ slot_of,
+                              int32_t* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = __ldg(q + i);
+    if (!coord_in_range(c.x, c.y, c.z, c.w)) {
+        atomicOr(reinterpret_cast<unsigned int*>(counts + 1), 1u);
+        slot_of[i] = -1;
+        return;
+    }
+    const unsigned long long key = pack_key(c.x, c.y, c.z, c.w);
+    unsigned long long s = hash_key(key) & mask;
+    while (true) {
+        unsigned long long prev = tab[s].key;  // cheap pre-read: most probes hit an owned slot
+        if (prev != key) {
+            if (prev != B2ME_KEY_EMPTY) {
+                s = (s + 1) & mask;
+                continue;
+            }
+            prev = atomicCAS(&tab[s].key, B2ME_KEY_EMPTY, key);
+            if (prev != B2ME_KEY_EMPTY && prev != key) {
+                s = (s + 1) & mask;
+                continue;
+            }
+        }
+        break;
+    }
+    atomicMin(&tab[s].val, (unsigned int)i);
+    slot_of[i] = (int32_t)s;
+}
+
+__global__ void k_first_flags(const HashSlot* __restrict__ tab, const int32_t* __restrict__ slot_of, int64_t n,
+                              int32_t* __restrict__ rank) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = slot_of[i];
+    rank[i] = (s >= 0 && tab[s].val == (unsigned int)i) ? 1 : 0;
+}
+
+// winners publish their row: table val <- row, coords, first index, (mode 0) features
+__global__ void k_assign_rows(const int4* __restrict__ q, const int32_t* __restrict__ slot_of,
+                              const int32_t* __restrict__ rank, const int32_t* __restrict__ counts, int64_t n,
+                              HashSlot* __restrict__ tab, int4* __restrict__ out_coords,
+                              int32_t* __restrict__ first_idx, const float* __restrict__ feats, int C, int mode,
+                              float* __restrict__ out_feats) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = rank[i];
+    const int32_t next = (i + 1 < n) ? rank[i + 1] : counts[0];
+    if (next == r) return;  // not the first point of its voxel
+    tab[slot_of[i]].val = (unsigned int)r;
+    out_coords[r] = q[i];
+    if (first_idx) first_idx[r] = (int32_t)i;
+    if (mode == 0 && C > 0) {
+        for (int c = 0; c < C; ++c) out_feats[(int64_t)r * C + c] = feats[i * C + c];
+    }
+}
+
+#define FIXED_ONE 4294967296.0  // 2^32
+
+__global__ void k_inverse_accumulate(const HashSlot* __restrict__ tab, const int32_t* __restrict__ slot_of,
+                                     int64_t n, int32_t* __restrict__ inverse, const float* __restrict__ feats,
+                                     int C, int mode, unsigned long long* __restrict__ fsum,
+                                     int32_t* __restrict__ cnt, int32_t* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t s = slot_of[i];
+    if (s < 0) {
+        inverse[i] = -1;
+        return;
+    }
+    const int32_t row = (int32_t)tab[s].val;
+    inverse[i] = row;
+    if (mode == 1 && C > 0) {
+        bool bad = false;
+        for (int c = 0; c < C; ++c) {
+            const float f = feats[i * C + c];
+            if (!(fabsf(f) < 1048576.f)) bad = true;  // also catches NaN
+            const long long fx = __double2ll_rn((double)f * FIXED_ONE);
+            atomicAdd(fsum + (int64_t)row * C + c, (unsigned long long)fx);
+        }
+        atomicAdd(cnt + row, 1);
+        if (bad) atomicOr(reinterpret_cast<unsigned int*>(counts + 1), 2u);
+    }
+}
+
+__global__ void k_mean_features(const unsigned long long* __restrict__ fsum, const int32_t* __restrict__ cnt,
+                                const int32_t* __restrict__ counts, int C, float* __restrict__ out_feats) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)counts[0] * C;
+    if (t >= total) return;
+    const int64_t row = t / C;
+    const double s = (double)(long long)fsum[t];
+    out_feats[t] = (float)((s / FIXED_ONE) / (double)cnt[row]);
+}
+
+extern "C" int64_t b2me_table_slots(int64_t n) {
+    int64_t s = 1024;
+    while (s < 2 * n) s <<= 1;
+    return s;
+}
+extern "C" size_t b2me_table_bytes(int64_t n) { return (size_t)b2me_table_slots(n) * sizeof(HashSlot); }
+
+struct UniqueWs {
+    int4* q;
+    int32_t* slot_of;
+    int32_t* rank;
+    void* scan;
+    unsigned long long* fsum;
+    int32_t* cnt;
+    size_t total;
+};
+
+static UniqueWs carve_unique_ws(void* ws, int64_t n, int C) {
+    UniqueWs w;
+    size_t off = 0;
+    char* base = reinterpret_cast<char*>(ws);
+    const int64_t n1 = n > 0 ? n : 1;
+    w.q = reinterpret_cast<int4*>(base + off);
+    off += align_up((size_t)n1 * sizeof(int4), 256);
+    w.slot_of = reinterpret_cast<int32_t*>(base + off);
+    off += align_up((size_t)n1 * sizeof(int32_t), 256);
+    w.rank = reinterpret_cast<int32_t*>(base + off);
+    off += align_up((size_t)n1 * sizeof(int32_t), 256);
+    w.scan = base + off;
+    off += scan_ws_bytes(n1);
+    w.fsum = reinterpret_cast<unsigned long long*>(base + off);
+    off += align_up((size_t)n1 * (size_t)(C > 0 ? C : 1) * sizeof(unsigned long long), 256);
+    w.cnt = reinterpret_cast<int32_t*>(base + off);
+    off += align_up((size_t)n1 * sizeof(int32_t), 256);
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t b2me_unique_workspace_bytes(int64_t n, int C) {
+    return carve_unique_ws(nullptr, n, C).total;
+}
+
+// common tail: q (int4 rows) -> table, rows, inverse
+static int unique_core(const int4* q, int64_t N, const float* feats, int C, int mode, int32_t* out_coords,
+                       float* out_feats, int32_t* inverse, int32_t* first_idx, int32_t* counts, void* table,
+                       size_t table_bytes, const UniqueWs& w, cudaStream_t s) {
+    const int64_t slots = b2me_table_slots(N);
+    if (table_bytes < (size_t)slots * sizeof(HashSlot)) return B2ME_EWORKSPACE;
+    HashSlot* tab = reinterpret_cast<HashSlot*>(table);
+    cudaMemsetAsync(tab, 0xFF, (size_t)slots * sizeof(HashSlot), s);
+    cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s);
+    if (N == 0) return B2ME_OK;
+    const int T = 256;
+    const unsigned G = (unsigned)ceil_div64(N, T);
+    k_hash_insert<<<G, T, 0, s>>>(q, N, tab, (unsigned long long)(slots - 1), w.slot_of, counts);
+    k_first_flags<<<G, T, 0, s>>>(tab, w.slot_of, N, w.rank);
+    int rc = exclusive_scan_i32(w.rank, N, counts, w.scan, s);
+    if (rc != B2ME_OK) return rc;
+    k_assign_rows<<<G, T, 0, s>>>(q, w.slot_of, w.rank, counts, N, tab, reinterpret_cast<int4*>(out_coords),
+                                  first_idx, feats, C, mode, out_feats);
+    if (mode == 1 && C > 0) {
+        cudaMemsetAsync(w.fsum, 0, (size_t)N * C * sizeof(unsigned long long), s);
+        cudaMemsetAsync(w.cnt, 0, (size_t)N * sizeof(int32_t), s);
+    }
+    k_inverse_accumulate<<<G, T, 0, s>>>(tab, w.slot_of, N, inverse, feats, C, mode, w.fsum, w.cnt, counts);
+    if (mode == 1 && C > 0) {
+        const int64_t total = N * C;  // upper bound on V*C; kernel bounds itself with counts[0]
+        k_mean_features<<<(unsigned)ceil_div64(total, T), T, 0, s>>>(w.fsum, w.cnt, counts, C, out_feats);
+    }
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+extern "C" int b2me_quantize_unique(const float* coords_f, const int32_t* coords_i, int64_t N, const float* feats,
+                                    int C, int mode, int32_t* out_coords, float* out_feats, int32_t* inverse,
+                                    int32_t* first_idx, int32_t* counts, void* table, size_t table_bytes, void* ws,
+                                    size_t ws_bytes, b2me_stream_t stream) {
+    if (N < 0 || C < 0 || (mode != 0 && mode != 1)) return B2ME_EINVAL;
+    if ((coords_f == nullptr) == (coords_i == nullptr) && N > 0) return B2ME_EINVAL;
+    if (!out_coords || !inverse || !counts || !table || !ws) return B2ME_EINVAL;
+    if (C > 0 && (!feats || !out_feats)) return B2ME_EINVAL;
+    if (N >= (int64_t)1 << 31) return B2ME_EINVAL;
+    UniqueWs w = carve_unique_ws(ws, N, C);
+    if (ws_bytes < w.total) return B2ME_EWORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int4* q = reinterpret_cast<const int4*>(coords_i);
+    if (coords_f && N > 0) {
+        k_quantize_float<<<(unsigned)ceil_div64(N, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(coords_f), N,
+                                                                      w.q);
+        q = w.q;
+    }
+    return unique_core(q, N, feats, C, mode, out_coords, out_feats, inverse, first_idx, counts, table, table_bytes, w,
+                       s);
+}
+
+__global__ void k_quantize_labels(const int32_t* __restrict__ labels, const int32_t* __restrict__ inverse,
+                                  const int32_t* __restrict__ first_idx, int64_t N, int32_t ignore_label,
+                                  int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t row = inverse[i];
+    if (row < 0) return;
+    const int32_t mine = labels[i];
+    const int32_t ref = labels[first_idx[row]];
+    if (mine != ref) out[row] = ignore_label;  // all writers store the same value
+}
+__global__ void k_init_labels(const int32_t* __restrict__ labels, const int32_t* __restrict__ first_idx, int64_t V,
+                              int32_t* __restrict__ out) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V) out[v] = labels[first_idx[v]];
+}
+
+extern "C" int b2me_quantize_labels(const int32_t* labels, const int32_t* inverse, const int32_t* first_idx,
+                                    int64_t N, int64_t V, int32_t ignore_label, int32_t* out_labels,
+                                    b2me_stream_t stream) {
+    if (!labels || !inverse || !first_idx || !out_labels || N < 0 || V < 0) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (V > 0) k_init_labels<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(labels, first_idx, V, out_labels);
+    if (N > 0)
+        k_quantize_labels<<<(unsigned)ceil_div64(N, 256), 256, 0, s>>>(labels, inverse, first_idx, N, ignore_label,
+                                                                       out_labels);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+extern "C" int b2me_stride_map(const int32_t* in_coords, int64_t V_in, int ts_out, int32_t* out_coords,
+                               int32_t* in2out, uint8_t* koff, int32_t* counts, void* table_out, size_t table_bytes,
+                               void* ws, size_t ws_bytes, b2me_stream_t stream) {
+    if (V_in < 0 || ts_out < 2 || (ts_out & 1)) return B2ME_EINVAL;
+    if (!in_coords || !out_coords || !in2out || !koff || !counts || !table_out || !ws) return B2ME_EINVAL;
+    UniqueWs w = carve_unique_ws(ws, V_in, 0);
+    if (ws_bytes < w.total) return B2ME_EWORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (V_in > 0)
+        k_quantize_stride<<<(unsigned)ceil_div64(V_in, 256), 256, 0, s>>>(reinterpret_cast<const int4*>(in_coords),
+                                                                          V_in, ts_out, w.q, koff);
+    return unique_core(w.q, V_in, nullptr, 0, 0, out_coords, nullptr, in2out, nullptr, counts, table_out, table_bytes,
+                       w, s);
+}
+
+__global__ void k_stride_kernel_maps(const int32_t* __restrict__ in2out, const uint8_t* __restrict__ koff,
+                                     int64_t V_in, int32_t* __restrict__ nbr_down, int32_t* __restrict__ nbr_up) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V_in) return;
+    const int32_t p = in2out[i];
+    const int k = koff[i];
+    if (p < 0) return;
+    if (nbr_down) nbr_down[(int64_t)p * 8 + k] = (int32_t)i;  // (parent, offset) has exactly one child
+    if (nbr_up) nbr_up[i * 8 + k] = p;
+}
+
+extern "C" int b2me_stride_kernel_maps(const int32_t* in2out, const uint8_t* koff, int64_t V_in, int64_t V_out,
+                                       int32_t* nbr_down, int32_t* nbr_up, b2me_stream_t stream) {
+    if (!in2out || !koff || V_in < 0 || V_out < 0) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (nbr_down && V_out > 0) cudaMemsetAsync(nbr_down, 0xFF, (size_t)V_out * 8 * sizeof(int32_t), s);
+    if (nbr_up && V_in > 0) cudaMemsetAsync(nbr_up, 0xFF, (size_t)V_in * 8 * sizeof(int32_t), s);
+    if (V_in > 0)
+        k_stride_kernel_maps<<<(unsigned)ceil_div64(V_in, 256), 256, 0, s>>>(in2out, koff, V_in, nbr_down, nbr_up);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K3
+// one thread per (voxel, offset): consecutive threads write consecutive nbr entries (full 128-B lines
+// per warp); the 27 threads of a voxel share its coordinate row through L1.
+__global__ void __launch_bounds__(256) k_kernel_map_k3(const int4* __restrict__ coords, int64_t V, int ts,
+                                                       const HashSlot* __restrict__ tab, unsigned long long mask,
+                                                       int32_t* __restrict__ nbr, uint32_t* __restrict__ tile_mask) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= V * 27) return;
+    const int64_t v = t / 27;
+    const int k = (int)(t - v * 27);
+    int32_t res;
+    if (k == 13) {
+        res = (int32_t)v;
+    } else {
+        const int4 c = __ldg(coords + v);
+        const int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        const int x = c.y + dx * ts, y = c.z + dy * ts, z = c.w + dz * ts;
+        res = -1;
+        if (coord_in_range(c.x, x, y, z)) res = (int32_t)table_lookup(tab, mask, pack_key(c.x, x, y, z));
+    }
+    nbr[t] = res;
+    if (tile_mask && res >= 0) {
+        const uint32_t bit = 1u << k;
+        volatile uint32_t* m = tile_mask + (v >> 7);
+        if (!(*m & bit)) atomicOr(tile_mask + (v >> 7), bit);
+    }
+}
+
+extern "C" int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* table, size_t table_bytes,
+                                  int32_t* nbr, uint32_t* tile_mask, b2me_stream_t stream) {
+    if (!coords || !table || !nbr || V < 0 || ts < 1) return B2ME_EINVAL;
+    const int64_t slots = (int64_t)(table_bytes / sizeof(HashSlot));
+    if (slots < 2 || (slots & (slots - 1))) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (V == 0) return B2ME_OK;
+    if (tile_mask) cudaMemsetAsync(tile_mask, 0, (size_t)ceil_div64(V, 128) * sizeof(uint32_t), s);
+    const int64_t total = V * 27;
+    k_kernel_map_k3<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(reinterpret_cast<const int4*>(coords), V, ts,
+                                                                     reinterpret_cast<const HashSlot*>(table),
+                                                                     (unsigned long long)(slots - 1), nbr, tile_mask);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

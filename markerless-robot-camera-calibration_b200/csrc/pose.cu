@@ -1,0 +1,438 @@
+// pose.cu — K9 batched 3x3 Kabsch/SVD and K10 batched point-to-point ICP (fp64 arithmetic on fp32 clouds).
+//
+// ICP: one CTA per frame. The frame's target (EE) points are binned once into a dense uniform grid
+// (<= 32^3 cells, cell >= 2 cm) by a preparation kernel; every iteration each thread takes source (CAD)
+// points, transforms them with the current 4x4 (fp64), finds the EXACT nearest target point within
+// max_corr by an expanding-ring search over the grid, and the block reduces the 17 sums Kabsch needs in
+// a fixed order. The loop and stopping rule restate Open3D's RegistrationICP as called by
+// utils/icp.py:65-71.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ 3x3 helpers
+__device__ inline void jacobi_eig3(double A[3][3], double V[3][3], double w[3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        const double offd = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+        if (offd <= 1e-300 || offd <= 1e-22 * diag) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = A[p][q];
+                if (fabs(apq) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {  // A <- A J
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {  // A <- J^T A
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
+}
+
+__device__ inline void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ inline double norm3(const double a[3]) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+
+// R = argmin sum |R a_i - b_i|^2 for H = sum a_i b_i^T (centred), det(R) = +1.
+// Equivalent to numpy's U,S,Vt = svd(H); R = Vt.T U.T with the last row of Vt flipped when det < 0
+// (utils/transformation.py:207-218): we build right-handed U and V from the two leading singular pairs.
+__device__ inline void kabsch_from_H(const double H[3][3], double R[3][3]) {
+    double A[3][3], V[3][3], w[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j];  // H^T H
+    jacobi_eig3(A, V, w);
+    int o[3] = {0, 1, 2};  // sort eigenvalues descending
+    if (w[o[0]] < w[o[1]]) { int t = o[0]; o[0] = o[1]; o[1] = t; }
+    if (w[o[1]] < w[o[2]]) { int t = o[1]; o[1] = o[2]; o[2] = t; }
+    if (w[o[0]] < w[o[1]]) { int t = o[0]; o[0] = o[1]; o[1] = t; }
+    double v0[3], v1[3], v2[3], u0[3], u1[3], u2[3];
+    for (int i = 0; i < 3; ++i) { v0[i] = V[i][o[0]]; v1[i] = V[i][o[1]]; }
+    cross3(v0, v1, v2);
+    for (int i = 0; i < 3; ++i) {
+        u0[i] = H[i][0] * v0[0] + H[i][1] * v0[1] + H[i][2] * v0[2];
+        u1[i] = H[i][0] * v1[0] + H[i][1] * v1[1] + H[i][2] * v1[2];
+    }
+    double n0 = norm3(u0);
+    if (n0 < 1e-300) {  // H == 0: identity
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i][j] = (i == j) ? 1.0 : 0.0;
+        return;
+    }
+    for (int i = 0; i < 3; ++i) u0[i] /= n0;
+    const double d = u1[0] * u0[0] + u1[1] * u0[1] + u1[2] * u0[2];
+    for (int i = 0; i < 3; ++i) u1[i] -= d * u0[i];
+    double n1 = norm3(u1);
+    if (n1 < 1e-14 * n0) {  // rank 1: any unit vector orthogonal to u0 (and the matching one for v)
+        double e[3] = {1, 0, 0};
+        if (fabs(u0[0]) > 0.9) { e[0] = 0; e[1] = 1; }
+        cross3(u0, e, u1);
+        n1 = norm3(u1);
+    }
+    for (int i = 0; i < 3; ++i) u1[i] /= n1;
+    cross3(u0, u1, u2);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i][j] = v0[i] * u0[j] + v1[i] * u1[j] + v2[i] * u2[j];  // V U^T
+}
+
+// ------------------------------------------------------------------------------------------ K9
+__global__ void k_kabsch_batched(const double* __restrict__ ref, const double* __restrict__ tgt,
+                                 const int32_t* __restrict__ npairs, int P, int kmax, double* __restrict__ out_R,
+                                 double* __restrict__ out_t) {
+    const int pb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pb >= P) return;
+    const int n = npairs[pb];
+    const double* a = ref + (int64_t)pb * kmax * 3;
+    const double* b = tgt + (int64_t)pb * kmax * 3;
+    double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) { ca[d] += a[i * 3 + d]; cb[d] += b[i * 3 + d]; }
+    const double inv = n > 0 ? 1.0 / n : 0.0;
+    for (int d = 0; d < 3; ++d) { ca[d] *= inv; cb[d] *= inv; }
+    double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < n; ++i)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) H[r][c] += (a[i * 3 + r] - ca[r]) * (b[i * 3 + c] - cb[c]);
+    double R[3][3];
+    kabsch_from_H(H, R);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) out_R[(int64_t)pb * 9 + r * 3 + c] = R[r][c];
+        out_t[(int64_t)pb * 3 + r] = cb[r] - (R[r][0] * ca[0] + R[r][1] * ca[1] + R[r][2] * ca[2]);
+    }
+}
+
+extern "C" int b2me_kabsch_batched(const double* ref, const double* tgt, const int32_t* npairs, int P, int kmax,
+                                   double* out_R, double* out_t, b2me_stream_t stream) {
+    if (!ref || !tgt || !npairs || !out_R || !out_t || P < 0 || kmax <= 0) return B2ME_EINVAL;
+    if (P == 0) return B2ME_OK;
+    k_kabsch_batched<<<(unsigned)((P + 63) / 64), 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ref, tgt, npairs, P,
+                                                                                                   kmax, out_R, out_t);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K10
+#define ICP_GRID 32
+#define ICP_CELLS (ICP_GRID * ICP_GRID * ICP_GRID)
+#define ICP_MIN_CELL 0.02
+#define ICP_THREADS 256
+
+struct IcpFrameGrid {
+    double origin[3];
+    double inv_h;
+    double h;
+    int dims[3];
+    int pad;
+};
+
+struct IcpWs {
+    IcpFrameGrid* grids;   // [F]
+    int32_t* cell_start;   // [F, ICP_CELLS + 1]
+    int32_t* cell_cursor;  // [F, ICP_CELLS]
+    float4* sorted;        // [T_total] xyz + original index bits
+    size_t total;
+};
+
+static IcpWs carve_icp_ws(void* ws, int64_t T_total, int F) {
+    IcpWs w;
+    char* base = reinterpret_cast<char*>(ws);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base + off;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const int F1 = F > 0 ? F : 1;
+    w.grids = reinterpret_cast<IcpFrameGrid*>(take((size_t)F1 * sizeof(IcpFrameGrid)));
+    w.cell_start = reinterpret_cast<int32_t*>(take((size_t)F1 * (ICP_CELLS + 1) * 4));
+    w.cell_cursor = reinterpret_cast<int32_t*>(take((size_t)F1 * ICP_CELLS * 4));
+    w.sorted = reinterpret_cast<float4*>(take((size_t)(T_total > 0 ? T_total : 1) * sizeof(float4)));
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t b2me_icp_workspace_bytes(int64_t T_total, int F) { return carve_icp_ws(nullptr, T_total, F).total; }
+
+__device__ __forceinline__ int icp_cell_coord(double v, double origin, double inv_h, int dim) {
+    int c = (int)floor((v - origin) * inv_h);
+    return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+
+// one block per frame: bbox -> grid, counting sort of the frame's target points by cell
+__global__ void __launch_bounds__(ICP_THREADS)
+k_icp_build_grid(const float* __restrict__ tgt, const int32_t* __restrict__ tgt_offsets,
+                 IcpFrameGrid* __restrict__ grids, int32_t* __restrict__ cell_start_all,
+                 int32_t* __restrict__ cursor_all, float4* __restrict__ sorted) {
+    __shared__ float smin[3][ICP_THREADS], smax[3][ICP_THREADS];
+    __shared__ IcpFrameGrid g;
+    __shared__ int scan_s[33];
+    __shared__ int carry_s;
+    const int f = blockIdx.x;
+    const int t0 = tgt_offsets[f], t1 = tgt_offsets[f + 1];
+    int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
+    int32_t* cursor = cursor_all + (int64_t)f * ICP_CELLS;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = t0 + threadIdx.x; i < t1; i += blockDim.x)
+        for (int a = 0; a < 3; ++a) {
+            const float v = tgt[(int64_t)i * 3 + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    for (int a = 0; a < 3; ++a) { smin[a][threadIdx.x] = mn[a]; smax[a][threadIdx.x] = mx[a]; }
+    __syncthreads();
+    for (int o = ICP_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int a = 0; a < 3; ++a) {
+                smin[a][threadIdx.x] = fminf(smin[a][threadIdx.x], smin[a][threadIdx.x + o]);
+                smax[a][threadIdx.x] = fmaxf(smax[a][threadIdx.x], smax[a][threadIdx.x + o]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double ext = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            const double e = (t1 > t0) ? (double)smax[a][0] - (double)smin[a][0] : 0.0;
+            ext = e > ext ? e : ext;
+        }
+        double h = ext / (ICP_GRID - 1);
+        if (h < ICP_MIN_CELL) h = ICP_MIN_CELL;
+        g.h = h;
+        g.inv_h = 1.0 / h;
+        for (int a = 0; a < 3; ++a) {
+            g.origin[a] = (t1 > t0) ? (double)smin[a][0] : 0.0;
+            const double e = (t1 > t0) ? (double)smax[a][0] - (double)smin[a][0] : 0.0;
+            int d = (int)floor(e / h) + 1;
+            g.dims[a] = d > ICP_GRID ? ICP_GRID : (d < 1 ? 1 : d);
+        }
+        g.pad = 0;
+        grids[f] = g;
+    }
+    __syncthreads();
+    const int ncell = g.dims[0] * g.dims[1] * g.dims[2];
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cell_start[c] = 0;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) cursor[c] = 0;
+    __syncthreads();
+    for (int i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+        const int cx = icp_cell_coord(tgt[(int64_t)i * 3], g.origin[0], g.inv_h, g.dims[0]);
+        const int cy = icp_cell_coord(tgt[(int64_t)i * 3 + 1], g.origin[1], g.inv_h, g.dims[1]);
+        const int cz = icp_cell_coord(tgt[(int64_t)i * 3 + 2], g.origin[2], g.inv_h, g.dims[2]);
+        atomicAdd(&cell_start[(cz * g.dims[1] + cy) * g.dims[0] + cx], 1);
+    }
+    __syncthreads();
+    // exclusive scan of ncell+1 counters by the block (chunks of blockDim)
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base <= ncell; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int v = (c <= ncell) ? cell_start[c] : 0;
+        // warp scan
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) scan_s[wp] = inc;
+        __syncthreads();
+        if (wp == 0) {
+            const int wv = lane < (ICP_THREADS / 32) ? scan_s[lane] : 0;
+            int winc = wv;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            scan_s[lane] = winc - wv;
+            if (lane == 31) scan_s[32] = winc;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (c <= ncell) cell_start[c] = inc - v + scan_s[wp] + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + scan_s[32];
+        __syncthreads();
+    }
+    for (int i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+        const float x = tgt[(int64_t)i * 3], y = tgt[(int64_t)i * 3 + 1], z = tgt[(int64_t)i * 3 + 2];
+        const int cx = icp_cell_coord(x, g.origin[0], g.inv_h, g.dims[0]);
+        const int cy = icp_cell_coord(y, g.origin[1], g.inv_h, g.dims[1]);
+        const int cz = icp_cell_coord(z, g.origin[2], g.inv_h, g.dims[2]);
+        const int cell = (cz * g.dims[1] + cy) * g.dims[0] + cx;
+        const int pos = atomicAdd(&cursor[cell], 1);
+        sorted[t0 + cell_start[cell] + pos] = make_float4(x, y, z, __int_as_float(i - t0));
+    }
+}
+
+#define ICP_NSUM 17  // count, sum d2, sum p(3), sum q(3), sum p q^T (9)
+
+__global__ void __launch_bounds__(ICP_THREADS)
+k_icp_p2p(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
+          const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
+          const float4* __restrict__ sorted, const double* __restrict__ init_T, double max_corr, int max_iter,
+          double rel_fitness, double rel_rmse, double* __restrict__ out_T, double* __restrict__ out_stats) {
+    __shared__ double T_s[16];
+    __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
+    __shared__ double tot[ICP_NSUM];
+    __shared__ int stop_s;
+    __shared__ IcpFrameGrid g;
+    const int f = blockIdx.x;
+    const int t0 = tgt_offsets[f];
+    const int nT = tgt_offsets[f + 1] - t0;
+    const int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
+    if (threadIdx.x < 16) T_s[threadIdx.x] = init_T[(int64_t)f * 16 + threadIdx.x];
+    if (threadIdx.x == 0) { g = grids[f]; stop_s = 0; }
+    __syncthreads();
+    const double R2 = max_corr * max_corr;
+    double prev_fit = 0.0, prev_rmse = 0.0, fit = 0.0, rmse = 0.0, ncorr = 0.0;
+    int iters = 0;
+
+    // eval #0 uses init; then for it = 0..max_iter-1: update from last eval, eval again, test convergence
+    for (int ev = 0; ev <= max_iter; ++ev) {
+        double acc[ICP_NSUM];
+#pragma unroll
+        for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
+        if (nT > 0) {
+            for (int i = threadIdx.x; i < S; i += blockDim.x) {
+                const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
+                const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
+                const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
+                const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
+                const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
+                const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
+                const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
+                double best = R2;  // strict '<' below: only neighbours inside the radius qualify
+                int best_j = 0x7FFFFFFF;
+                double bx = 0, by = 0, bz = 0;
+                const int rmax = ICP_GRID;
+                for (int r = 0; r <= rmax; ++r) {
+                    // every point in ring r is at least (r-1)*h away
+                    if (r >= 2) {
+                        const double lb = (double)(r - 1) * g.h;
+                        if (lb * lb >= best) break;
+                    }
+                    const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+                    if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
+                    for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
+                        const bool zf = (z == z0 || z == z1);
+                        for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
+                            const bool yf = (y == y0 || y == y1);
+                            const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
+                            for (int x = x0; x <= x1; x += xstep) {
+                                if (x < 0 || x >= g.dims[0]) continue;
+                                const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
+                                const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
+                                for (int s = s0; s < s1; ++s) {
+                                    const float4 q = __ldg(sorted + t0 + s);
+                                    const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
+                                    const double d2 = dx * dx + dy * dy + dz * dz;
+                                    const int j = __float_as_int(q.w);
+                                    if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
+                                        best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (best_j != 0x7FFFFFFF) {
+                    acc[0] += 1.0; acc[1] += best;
+                    acc[2] += px; acc[3] += py; acc[4] += pz;
+                    acc[5] += bx; acc[6] += by; acc[7] += bz;
+                    acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
+                    acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
+                    acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
+                }
+            }
+        }
+        // fixed-order block reduction
+#pragma unroll
+        for (int q = 0; q < ICP_NSUM; ++q) {
+            double v = acc[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < ICP_NSUM) {
+            double v = 0.0;
+            for (int wv = 0; wv < ICP_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+            tot[threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ncorr = tot[0];
+            fit = S > 0 ? ncorr / (double)S : 0.0;
+            rmse = ncorr > 0 ? sqrt(tot[1] / ncorr) : 0.0;
+            bool stop = false;
+            if (ev > 0) {
+                iters = ev;
+                if (fabs(prev_fit - fit) < rel_fitness && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
+            }
+            if (ev == max_iter) stop = true;
+            if (!stop) {
+                prev_fit = fit; prev_rmse = rmse;
+                if (ncorr > 0) {
+                    // update = Kabsch(transformed source -> matched targets) (Eigen::umeyama without scaling)
+                    const double n = ncorr;
+                    const double mp[3] = {tot[2] / n, tot[3] / n, tot[4] / n};
+                    const double mq[3] = {tot[5] / n, tot[6] / n, tot[7] / n};
+                    double H[3][3], R[3][3];
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) H[r][c] = tot[8 + r * 3 + c] - n * mp[r] * mq[c];
+                    kabsch_from_H(H, R);
+                    double t[3];
+                    for (int r = 0; r < 3; ++r) t[r] = mq[r] - (R[r][0] * mp[0] + R[r][1] * mp[1] + R[r][2] * mp[2]);
+                    double Tn[12];
+                    for (int r = 0; r < 3; ++r) {
+                        for (int c = 0; c < 4; ++c)
+                            Tn[r * 4 + c] = R[r][0] * T_s[c] + R[r][1] * T_s[4 + c] + R[r][2] * T_s[8 + c];
+                        Tn[r * 4 + 3] += t[r];
+                    }
+                    for (int q = 0; q < 12; ++q) T_s[q] = Tn[q];
+                }
+            }
+            stop_s = stop ? 1 : 0;
+        }
+        __syncthreads();
+        if (stop_s) break;
+    }
+    if (threadIdx.x < 16) out_T[(int64_t)f * 16 + threadIdx.x] = T_s[threadIdx.x];
+    if (threadIdx.x == 0) {
+        out_stats[(int64_t)f * 4 + 0] = fit;
+        out_stats[(int64_t)f * 4 + 1] = rmse;
+        out_stats[(int64_t)f * 4 + 2] = (double)iters;
+        out_stats[(int64_t)f * 4 + 3] = ncorr;
+    }
+}
+
+extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
+                                    const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
+                                    double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* out_T,
+                                    double* out_stats, void* ws, size_t ws_bytes, b2me_stream_t stream) {
+    if (!source_xyz || !target_xyz || !tgt_offsets || !init_T || !out_T || !out_stats || !ws) return B2ME_EINVAL;
+    if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
+    if (F == 0) return B2ME_OK;
+    IcpWs w = carve_icp_ws(ws, T_total, F);
+    if (ws_bytes < w.total) return B2ME_EWORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    k_icp_build_grid<<<(unsigned)F, ICP_THREADS, 0, s>>>(target_xyz, tgt_offsets, w.grids, w.cell_start, w.cell_cursor,
+                                                         w.sorted);
+    k_icp_p2p<<<(unsigned)F, ICP_THREADS, 0, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, init_T,
+                                                  max_corr, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

@@ -1,0 +1,273 @@
+// spconv_simt.cu — K4a: fp32-accumulate SIMT gather-GEMM (output-stationary, no scatter/atomics),
+// plus the small element-wise / gather / small-N linear kernels of the ME-compatible layer.
+//
+// The SIMT convolution is the exact-fp32 path (parity tolerance 1e-3, SURVEY.md north star) and the
+// path for shapes the tcgen05 kernel does not take (Cin = 3 stem, odd channel counts).
+#include "common.cuh"
+
+#define SM_BM 64
+#define SM_BN 64
+#define SM_BK 16
+#define SM_THREADS 256
+
+// out[o,:] = act((sum_kk A[o,kk] * W[kk,:]) * scale + shift + residual), kk = k*Cin + c flattened
+__global__ void __launch_bounds__(SM_THREADS)
+k_spconv_simt(const void* __restrict__ in1, int Cin1, const void* __restrict__ in2, int Cin2, int in_dtype,
+              const float* __restrict__ W, const int32_t* __restrict__ nbr, int K, int64_t V_out, int Cout,
+              const float* __restrict__ scale, const float* __restrict__ shift, const void* __restrict__ residual,
+              int res_dtype, int act, float slope, void* __restrict__ out, int out_dtype) {
+    __shared__ float As[SM_BK][SM_BM + 4];
+    __shared__ float Bs[SM_BK][SM_BN + 4];
+    const int Cin = Cin1 + Cin2;
+    const int KK = K * Cin;
+    const int64_t row0 = (int64_t)blockIdx.x * SM_BM;
+    const int n0 = blockIdx.y * SM_BN;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int a_r = tid >> 2;         // 0..63
+    const int a_k = (tid & 3) * 4;    // 0,4,8,12
+    const int b_k = tid >> 4;         // 0..15
+    const int b_n = (tid & 15) * 4;   // 0..60
+    const int64_t a_row = row0 + a_r;
+
+    for (int kk0 = 0; kk0 < KK; kk0 += SM_BK) {
+        // ---- gather A
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = kk0 + a_k + j;
+            float v = 0.f;
+            if (kk < KK && a_row < V_out) {
+                const int k = kk / Cin;
+                const int c = kk - k * Cin;
+                const int64_t idx = nbr ? (int64_t)nbr[a_row * K + k] : a_row;
+                if (idx >= 0) {
+                    v = (c < Cin1) ? load_as_f32(in1, in_dtype, idx * Cin1 + c)
+                                   : load_as_f32(in2, in_dtype, idx * Cin2 + (c - Cin1));
+                }
+            }
+            As[a_k + j][a_r] = v;
+        }
+        // ---- load B
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = kk0 + b_k;
+            const int n = n0 + b_n + j;
+            Bs[b_k][b_n + j] = (kk < KK && n < Cout) ? __ldg(W + (int64_t)kk * Cout + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SM_BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + ty * 4 + i;
+        if (row >= V_out) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= Cout) continue;
+            float v = acc[i][j];
+            if (scale) v *= scale[n];
+            if (shift) v += shift[n];
+            if (residual) v += load_as_f32(residual, res_dtype, row * Cout + n);
+            v = apply_act(v, act, slope);
+            store_from_f32(out, out_dtype, row * Cout + n, v);
+        }
+    }
+}
+
+extern "C" int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, int Cin2, int in_dtype,
+                                    const float* W, const int32_t* nbr, int K, int64_t V_out, int Cout,
+                                    const float* scale, const float* shift, const void* residual, int res_dtype,
+                                    int act, float slope, void* out, int out_dtype, b2me_stream_t stream) {
+    if (!in1 || !W || !out || Cin1 <= 0 || Cin2 < 0 || K <= 0 || Cout <= 0 || V_out < 0) return B2ME_EINVAL;
+    if (Cin2 > 0 && !in2) return B2ME_EINVAL;
+    if (!nbr && K != 1) return B2ME_EINVAL;
+    if (V_out == 0) return B2ME_OK;
+    dim3 grid((unsigned)ceil_div64(V_out, SM_BM), (unsigned)((Cout + SM_BN - 1) / SM_BN));
+    k_spconv_simt<<<grid, SM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        in1, Cin1, in2, Cin2, in_dtype, W, nbr, K, V_out, Cout, scale, shift, residual, res_dtype, act, slope, out,
+        out_dtype);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+__global__ void k_affine_act(const void* __restrict__ in, int in_dtype, int64_t total, int C,
+                             const float* __restrict__ scale, const float* __restrict__ shift,
+                             const void* __restrict__ residual, int res_dtype, int act, float slope,
+                             void* __restrict__ out, int out_dtype) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        float v = load_as_f32(in, in_dtype, t);
+        if (scale) v *= scale[c];
+        if (shift) v += shift[c];
+        if (residual) v += load_as_f32(residual, res_dtype, t);
+        store_from_f32(out, out_dtype, t, apply_act(v, act, slope));
+    }
+}
+
+extern "C" int b2me_affine_act(const void* in, int in_dtype, int64_t V, int C, const float* scale,
+                               const float* shift, const void* residual, int res_dtype, int act, float slope,
+                               void* out, int out_dtype, b2me_stream_t stream) {
+    if (!in || !out || V < 0 || C <= 0) return B2ME_EINVAL;
+    const int64_t total = V * C;
+    if (total == 0) return B2ME_OK;
+    int64_t blocks = ceil_div64(total, 256);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_affine_act<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        in, in_dtype, total, C, scale, shift, residual, res_dtype, act, slope, out, out_dtype);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+__global__ void k_convert(const void* __restrict__ in, int in_dtype, void* __restrict__ out, int out_dtype,
+                          int64_t n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        store_from_f32(out, out_dtype, t, load_as_f32(in, in_dtype, t));
+}
+
+extern "C" int b2me_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t n,
+                            b2me_stream_t stream) {
+    if (!in || !out || n < 0) return B2ME_EINVAL;
+    if (n == 0) return B2ME_OK;
+    int64_t blocks = ceil_div64(n, 256);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_convert<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, in_dtype, out, out_dtype, n);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K5 small-N linear
+// one warp per voxel row; lanes stride the input channels (coalesced row read), Cout <= 16 partial sums
+// per lane, fixed-order butterfly reduction (deterministic), lane 0 writes logits and the arg-max.
+#define LS_MAX_COUT 16
+__global__ void __launch_bounds__(256)
+k_linear_small(const void* __restrict__ in, int in_dtype, int64_t V, int Cin, const float* __restrict__ Wt,
+               const float* __restrict__ bias, int Cout, float* __restrict__ out_logits,
+               uint8_t* __restrict__ out_argmax) {
+    extern __shared__ float w_s[];  // [Cout][Cin]
+    for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) w_s[i] = Wt[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < V;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        float acc[LS_MAX_COUT];
+#pragma unroll
+        for (int o = 0; o < LS_MAX_COUT; ++o) acc[o] = 0.f;
+        for (int c = lane; c < Cin; c += 32) {
+            const float x = load_as_f32(in, in_dtype, row * Cin + c);
+#pragma unroll
+            for (int o = 0; o < LS_MAX_COUT; ++o)
+                if (o < Cout) acc[o] = fmaf(x, w_s[o * Cin + c], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < LS_MAX_COUT; ++o) {
+            if (o < Cout) {
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+            }
+        }
+        if (lane == 0) {
+            float best = -INFINITY;
+            int besti = 0;
+#pragma unroll
+            for (int o = 0; o < LS_MAX_COUT; ++o) {
+                if (o < Cout) {
+                    const float v = acc[o] + (bias ? bias[o] : 0.f);
+                    if (out_logits) out_logits[row * Cout + o] = v;
+                    if (v > best) {  // strict: lowest index wins ties
+                        best = v;
+                        besti = o;
+                    }
+                }
+            }
+            if (out_argmax) out_argmax[row] = (uint8_t)besti;
+        }
+    }
+}
+
+extern "C" int b2me_linear_small(const void* in, int in_dtype, int64_t V, int Cin, const float* Wt,
+                                 const float* bias, int Cout, float* out_logits, uint8_t* out_argmax,
+                                 b2me_stream_t stream) {
+    if (!in || !Wt || V < 0 || Cin <= 0 || Cout <= 0 || Cout > LS_MAX_COUT) return B2ME_EINVAL;
+    const size_t smem = (size_t)Cout * Cin * sizeof(float);
+    if (smem > 200 * 1024) return B2ME_EUNSUPPORTED;
+    if (V == 0) return B2ME_OK;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(k_linear_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = ceil_div64(V, 8);
+    if (blocks > B2ME_NUM_SMS * 8) blocks = B2ME_NUM_SMS * 8;
+    k_linear_small<<<(unsigned)blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        in, in_dtype, V, Cin, Wt, bias, Cout, out_logits, out_argmax);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// ------------------------------------------------------------------------------------------ gathers
+__global__ void k_gather_words(const uint32_t* __restrict__ in, int words_per_row, const int32_t* __restrict__ index,
+                               int64_t total_words, uint32_t* __restrict__ out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_words;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / words_per_row;
+        const int w = (int)(t - i * words_per_row);
+        const int32_t src = index[i];
+        out[t] = src >= 0 ? in[(int64_t)src * words_per_row + w] : 0u;
+    }
+}
+
+extern "C" int b2me_gather_rows(const void* in, int dtype, int C, const int32_t* index, int64_t N, void* out,
+                                b2me_stream_t stream) {
+    if (!in || !index || !out || C <= 0 || N < 0) return B2ME_EINVAL;
+    const int row_bytes = C * (dtype == B2ME_BF16 ? 2 : 4);
+    if (row_bytes % 4) return B2ME_EUNSUPPORTED;
+    if (N == 0) return B2ME_OK;
+    const int wpr = row_bytes / 4;
+    const int64_t total = N * wpr;
+    int64_t blocks = ceil_div64(total, 256);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_gather_words<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t*>(in), wpr, index, total, reinterpret_cast<uint32_t*>(out));
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+__global__ void k_gather_labels(const uint8_t* __restrict__ lab, const int32_t* __restrict__ inverse, int64_t N,
+                                uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = inverse[i];
+        out[i] = v >= 0 ? lab[v] : (uint8_t)0;
+    }
+}
+
+extern "C" int b2me_gather_labels(const uint8_t* voxel_labels, const int32_t* inverse, int64_t N, uint8_t* out,
+                                  b2me_stream_t stream) {
+    if (!voxel_labels || !inverse || !out || N < 0) return B2ME_EINVAL;
+    if (N == 0) return B2ME_OK;
+    int64_t blocks = ceil_div64(N, 256);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_gather_labels<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(voxel_labels, inverse, N,
+                                                                                         out);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

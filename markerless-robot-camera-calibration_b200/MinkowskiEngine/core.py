@@ -41,6 +41,7 @@ class SparseTensorOperationMode(Enum):
 class _State:
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
+    profile = None  # bench.py hook, see ops._profile_conv
 
 
 def set_compute_dtype(dtype):
@@ -61,6 +62,12 @@ def reset_launch_count():
 
 def launch_count():
     return _State.launches
+
+
+def set_profile(mode):
+    """None | 'census' | 'events' -> the record list that ops._profile_conv appends to."""
+    _State.profile = None if mode is None else dict(mode=mode, records=[])
+    return None if mode is None else _State.profile["records"]
 
 
 def _count(n=1):

@@ -92,6 +92,22 @@ def _run_elt(p):
     return out
 
 
+def _profile_conv(kind, p, Cin):
+    """bench.py hook: 'census' records the algorithmic work of every convolution launch (pairs = sum_k P_k),
+    'events' brackets the launch with CUDA events on the launching stream."""
+    prof = _State.profile
+    if prof is None:
+        return None
+    if prof["mode"] == "census":
+        pairs = int((p.nbr >= 0).sum().item()) if p.nbr is not None else int(p.V_out)
+        prof["records"].append(dict(kind=kind, K=p.K, Cin=Cin, Cout=p.Cout, V_out=int(p.V_out), pairs=pairs))
+        return None
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record()
+    prof["records"].append(ev)
+    return ev
+
+
 def _run_conv(p):
     srcs = p.src
     f1 = srcs[0]._materialize()
@@ -112,9 +128,12 @@ def _run_conv(p):
             res = _as_dtype(res, torch.bfloat16)
         packed = _weight_packed(p.module, K, Cin1, Cin2, Cout)
         out = torch.empty((V_out, Cout), dtype=torch.bfloat16, device=dev)
+        ev = _profile_conv("tc", p, Cin1 + Cin2)
         check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, ptr(packed), ptr(p.nbr), None, K, V_out, Cout,
                                      ptr(p.scale), ptr(p.shift), ptr(res), p.act, p.slope, ptr(out), _lib.BF16,
                                      stream()), "spconv_fwd_tc")
+        if ev is not None:
+            ev[1].record()
         _count(1)
         return out
     # SIMT fp32-accumulate path
@@ -123,10 +142,13 @@ def _run_conv(p):
     W = _weight_f32(p.module)
     out_dtype = torch.float32 if (small_out or cdt == torch.float32) else torch.bfloat16
     out = torch.empty((V_out, Cout), dtype=out_dtype, device=dev)
+    ev = _profile_conv("simt", p, Cin1 + Cin2)
     check(lib.b2me_spconv_fwd_simt(ptr(f1), Cin1, ptr(f2), Cin2, dtype_code(f1.dtype), ptr(W), ptr(p.nbr), K, V_out,
                                    Cout, ptr(p.scale), ptr(p.shift), ptr(res),
                                    dtype_code(res.dtype) if res is not None else 0, p.act, p.slope, ptr(out),
                                    dtype_code(out_dtype), stream()), "spconv_fwd_simt")
+    if ev is not None:
+        ev[1].record()
     _count(1)
     return out
 

@@ -1,0 +1,107 @@
+"""Point-to-point ICP with the interface of utils/icp.py (get_point2point_matcher -> match(ee_points,
+pose_initial)), batched over frames on the GPU (K10 + K9). The CAD source cloud is read from
+app/hand_files/hand.pcd-style binary PCD files or sampled (seeded) from an OBJ mesh."""
+import os
+
+import numpy as np
+import torch
+
+from MinkowskiEngine._lib import lib, check, ptr, stream
+from .transformation import get_transformation_matrix, get_pose_from_matrix
+
+ICP_THRESHOLD = 0.1      # utils/icp.py:42
+ICP_MAX_ITER = 30        # Open3D ICPConvergenceCriteria defaults
+ICP_REL_FITNESS = 1e-6
+ICP_REL_RMSE = 1e-6
+
+
+def read_pcd_xyz(path):
+    """minimal PCD reader (ascii / binary, x y z as the first three float32 fields)."""
+    with open(path, "rb") as fp:
+        header = {}
+        while True:
+            line = fp.readline().decode("ascii", "replace").strip()
+            if not line or line.startswith("#"):
+                continue
+            k, *v = line.split()
+            header[k] = v
+            if k == "DATA":
+                break
+        n = int(header["POINTS"][0])
+        sizes = [int(s) for s in header["SIZE"]]
+        counts = [int(c) for c in header.get("COUNT", ["1"] * len(sizes))]
+        stride = sum(s * c for s, c in zip(sizes, counts))
+        if header["DATA"][0] == "binary":
+            raw = np.frombuffer(fp.read(n * stride), dtype=np.uint8).reshape(n, stride)
+            return raw[:, :12].copy().view(np.float32).reshape(n, 3).astype(np.float32)
+        if header["DATA"][0] == "ascii":
+            return np.loadtxt(fp, dtype=np.float32)[:, :3]
+        raise ValueError("compressed PCD is not supported")
+
+
+def read_obj(path):
+    verts, faces = [], []
+    with open(path) as fp:
+        for line in fp:
+            if line.startswith("v "):
+                verts.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith("f "):
+                idx = [int(tok.split("/")[0]) - 1 for tok in line.split()[1:]]
+                for i in range(1, len(idx) - 1):
+                    faces.append([idx[0], idx[i], idx[i + 1]])
+    return np.asarray(verts, np.float64), np.asarray(faces, np.int64)
+
+
+def sample_mesh_uniform(verts, faces, n, seed=13):
+    """area-weighted uniform surface sampling (seeded stand-in for Open3D's unseeded sampler, utils/icp.py:26-31)."""
+    rng = np.random.default_rng(seed)
+    a, b, c = verts[faces[:, 0]], verts[faces[:, 1]], verts[faces[:, 2]]
+    area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
+    tri = rng.choice(len(faces), size=n, p=area / area.sum())
+    r1, r2 = np.sqrt(rng.random(n)), rng.random(n)
+    w = np.stack((1 - r1, r1 * (1 - r2), r1 * r2), axis=1)
+    return (w[:, :1] * a[tri] + w[:, 1:2] * b[tri] + w[:, 2:] * c[tri]).astype(np.float32)
+
+
+def load_cad_points(cad_name, n_points=8192, seed=13):
+    if cad_name.endswith(".pcd"):
+        return read_pcd_xyz(cad_name)
+    v, f = read_obj(cad_name)
+    pts = sample_mesh_uniform(v, f, n_points, seed)
+    # utils/icp.py:34: `x > 0.0 * (z > -0.02)` == `x > 0` by operator precedence
+    return pts[pts[:, 0] > 0.0]
+
+
+def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD, max_iter=ICP_MAX_ITER,
+                    rel_fitness=ICP_REL_FITNESS, rel_rmse=ICP_REL_RMSE):
+    """source [S,3] f32 CUDA (CAD); targets [T_total,3] f32 CUDA; tgt_offsets [F+1]; init_T [F,4,4] f64.
+    Returns (T [F,4,4] f64, stats [F,4] f64 = fitness, inlier_rmse, iterations, correspondences)."""
+    source = source.to(torch.float32).contiguous()
+    targets = targets.to(torch.float32).contiguous()
+    dev = source.device
+    offs = torch.as_tensor(tgt_offsets, dtype=torch.int32, device=dev).contiguous()
+    F = offs.numel() - 1
+    init_T = init_T.to(dev, torch.float64).contiguous().view(F, 16)
+    out_T = torch.empty((F, 16), dtype=torch.float64, device=dev)
+    stats = torch.empty((F, 4), dtype=torch.float64, device=dev)
+    ws = torch.empty((lib.b2me_icp_workspace_bytes(targets.shape[0], F),), dtype=torch.uint8, device=dev)
+    check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
+                                   ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
+                                   ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")
+    return out_T.view(F, 4, 4), stats
+
+
+def get_point2point_matcher(cad_name, n_points=8192, seed=13):
+    """utils/icp.py:13-83: returns match(ee_points, pose_initial) -> refined pose (x,y,z,qw,qx,qy,qz)."""
+    cad = torch.from_numpy(load_cad_points(cad_name, n_points, seed)).cuda()
+
+    def match(ee_points, pose_initial):
+        if ee_points is None or pose_initial is None:
+            return pose_initial
+        T0 = torch.from_numpy(get_transformation_matrix(np.asarray(pose_initial, dtype=np.float64))).unsqueeze(0)
+        tgt = torch.as_tensor(np.asarray(ee_points, dtype=np.float32)).cuda()
+        T, _ = icp_p2p_batched(cad, tgt, [0, tgt.shape[0]], T0)
+        return get_pose_from_matrix(T[0].cpu().numpy())
+
+    match.cad_points = cad
+    return match

@@ -1,0 +1,297 @@
+"""Batched mirror of app/inference_engine.py InferenceEngine.predict (:281-382) on one GPU.
+
+The reference runs one frame at a time with >= 4 device->host syncs and CPU stages (sklearn clustering,
+Open3D ICP) in between. Here a batch of frames goes through every stage on the device:
+
+  normalise colours (utils/preprocess.py:20-37)             torch elementwise (plumbing)
+  predict_segmentation (:395-435)                           K1 voxelise -> MinkUNet (K2-K4) -> head (K5) ->
+                                                            per-point labels (fused slice+argmax) -> K7 largest
+                                                            EE cluster per frame
+  gate on ee_point_counts_threshold (:295)                  host, from the per-frame EE counts
+  predict_rotation (:437-457)                               K1 + RobotNetEncode trunk (K2-K4, K6) on the EE crops
+  predict_translation "magic" (:459-489)                    fused min/max reduction kernel
+  predict_key_points, ME branch (:539-555)                  K1 + key-point seg-net + K8a
+  predict_pose_from_kp (:384-393)                           K9 batched Kabsch
+  match_icp x2 (:358-362, utils/icp.py:50-81)               K10 batched ICP (+K9)
+  get_base2cam_pose (:366-369)                              host 4x4 algebra
+
+Frames are independent, so multi-GPU runs shard frames across ranks (dist.py) and all-gather the poses.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+import MinkowskiEngine as ME
+from MinkowskiEngine._lib import lib, check, ptr, stream
+
+from . import output as out_utils
+from .icp import icp_p2p_batched
+from .synthetic import REFERENCE_KEY_POINTS
+from .transformation import (rigid_transform_3D_batched, get_pose_from_matrix, get_base2cam_pose)
+
+
+@dataclass
+class PipelineConfig:
+    """thresholds and scales of config/default.yaml:136-191 (INFERENCE section)."""
+    seg_scale: float = 200.0
+    rot_scale: float = 200.0
+    kp_scale: float = 800.0
+    ee_point_counts_threshold: int = 512
+    cluster_dist: float = 0.06
+    kp_conf_threshold: float = 0.75
+    icp_enabled: bool = True
+    rot_center_at_origin: bool = True
+    kp_center_at_origin: bool = True
+    translation_x_offset: float = -0.015
+
+
+@dataclass
+class FrameResult:
+    """ResultDTO of app/dto.py:37-47 (poses are x,y,z,qw,qx,qy,qz)."""
+    segmentation: np.ndarray
+    ee_pose: Optional[np.ndarray] = None
+    base_pose: Optional[np.ndarray] = None
+    key_points: list = field(default_factory=list)
+    key_points_pose: Optional[np.ndarray] = None
+    key_points_base_pose: Optional[np.ndarray] = None
+    is_confident: bool = False
+    icp_stats: Optional[np.ndarray] = None
+
+
+def normalize_colors_(rgb):
+    """utils/preprocess.py:20-37 on a device tensor (the min-max branch for negative inputs is not taken by
+    valid colours)."""
+    if rgb.numel() and float(rgb.max()) > 2:
+        rgb = rgb / 255.0
+    return rgb - 0.5
+
+
+def batch_frames(frames, device, pinned=None):
+    """list of (points [N_i,3] f32, rgb [N_i,3] f32) host arrays -> device tensors + frame offsets.
+    One H2D copy per tensor per batch (from pinned staging when given)."""
+    counts = [len(f[0]) for f in frames]
+    offs = np.zeros(len(frames) + 1, dtype=np.int64)
+    np.cumsum(counts, out=offs[1:])
+    N = int(offs[-1])
+    if pinned is None:
+        pts = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+        rgb = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+        bidx = torch.empty((N,), dtype=torch.float32).pin_memory()
+    else:
+        pts, rgb, bidx = pinned[0][:N], pinned[1][:N], pinned[2][:N]
+    for i, f in enumerate(frames):
+        pts[offs[i]:offs[i + 1]] = torch.as_tensor(f[0])
+        rgb[offs[i]:offs[i + 1]] = torch.as_tensor(f[1])
+        bidx[offs[i]:offs[i + 1]] = float(i)
+    return (pts.to(device, non_blocking=True), rgb.to(device, non_blocking=True),
+            bidx.to(device, non_blocking=True), offs)
+
+
+def _field(points, rgb, bidx, scale, nb):
+    coords = torch.cat((bidx.unsqueeze(1), points * scale), dim=1)  # fp32 multiply, then K1 floors (§8a a2)
+    f = ME.TensorField(features=rgb, coordinates=coords,
+                       quantization_mode=ME.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE,
+                       minkowski_algorithm=ME.MinkowskiAlgorithm.SPEED_OPTIMIZED, device=points.device)
+    f._nb = nb
+    return f
+
+
+def segment_points(model, points, rgb, bidx, nb, scale):
+    """predict_segmentation up to the per-point arg-max: returns labels [N] uint8 (device)."""
+    fld = _field(points, rgb, bidx, scale, nb)
+    sp = fld.sparse()
+    out = model(sp)
+    logits = out.F  # [V, C] f32 voxel logits (K5)
+    V, C = logits.shape
+    vlab = torch.empty((max(V, 1),), dtype=torch.uint8, device=logits.device)
+    # slice + arg-max fused: arg-max per voxel, then 1 byte per point through the inverse map
+    check(lib.b2me_linear_small(ptr(logits), 0, V, C, ptr(_eye(C, logits.device)), None, C, None, ptr(vlab), stream()),
+          "argmax")
+    N = points.shape[0]
+    labels = torch.empty((max(N, 1),), dtype=torch.uint8, device=logits.device)
+    check(lib.b2me_gather_labels(ptr(vlab), ptr(fld.inverse_mapping), N, ptr(labels), stream()), "gather_labels")
+    return labels[:N], fld, out
+
+
+_EYES = {}
+
+
+def _eye(C, device):
+    k = (C, str(device))
+    if k not in _EYES:
+        _EYES[k] = torch.eye(C, dtype=torch.float32, device=device).contiguous()
+    return _EYES[k]
+
+
+def _segment_minmax(points, seg_ids, S):
+    mn = torch.full((S, 3), float("inf"), device=points.device)
+    mx = torch.full((S, 3), float("-inf"), device=points.device)
+    idx = seg_ids.unsqueeze(1).expand(-1, 3)
+    mn.scatter_reduce_(0, idx, points, reduce="amin")
+    mx.scatter_reduce_(0, idx, points, reduce="amax")
+    return mn, mx
+
+
+class BatchedInferenceEngine:
+    def __init__(self, seg_model, rot_model=None, kp_model=None, cad_points=None, config=None,
+                 reference_key_points=REFERENCE_KEY_POINTS):
+        self.seg_model = seg_model.eval()
+        self.rot_model = rot_model.eval() if rot_model is not None else None
+        self.kp_model = kp_model.eval() if kp_model is not None else None
+        self.cad = cad_points
+        self.cfg = config or PipelineConfig()
+        self.ref_kp = torch.as_tensor(np.asarray(reference_key_points, dtype=np.float64))
+
+    @torch.no_grad()
+    def segment(self, points, rgb, bidx, offs):
+        """labels after the EE largest-cluster filter (app/inference_engine.py:419-433), per-frame EE counts."""
+        nb = len(offs) - 1
+        labels, _, _ = segment_points(self.seg_model, points, normalize_colors_(rgb), bidx, nb, self.cfg.seg_scale)
+        return self.filter_ee(points, labels, bidx, nb)
+
+    def filter_ee(self, points, labels, bidx, nb):
+        ee_idx = torch.nonzero(labels == 2).flatten()
+        labels = torch.where(labels == 2, torch.ones_like(labels), labels)
+        if ee_idx.numel() == 0:
+            return labels, ee_idx, torch.zeros(nb + 1, dtype=torch.int64)
+        ee_frame = bidx[ee_idx].long()
+        counts = torch.bincount(ee_frame, minlength=nb)
+        ee_offs = torch.zeros(nb + 1, dtype=torch.int64, device=points.device)
+        ee_offs[1:] = torch.cumsum(counts, 0)
+        ee_offs_h = ee_offs.cpu()
+        ee_pts = points[ee_idx].contiguous()
+        mask, _ = out_utils.largest_cluster_mask(ee_pts, ee_offs_h.to(torch.int32).numpy(), self.cfg.cluster_dist)
+        keep = ee_idx[mask.bool()]
+        labels[keep] = 2
+        kcounts = torch.bincount(bidx[keep].long(), minlength=nb)
+        koffs = torch.zeros(nb + 1, dtype=torch.int64)
+        koffs[1:] = torch.cumsum(kcounts, 0).cpu()
+        return labels, keep, koffs
+
+    @torch.no_grad()
+    def pose_from_ee(self, points, rgb_norm, ee_idx, ee_offs, ee2base_poses=None, kp_conf_threshold=None):
+        """rotation + translation + key points + Kabsch + ICP for the frames whose EE crop passes the gate.
+        ee_idx: rows of the EE points (frame-sorted), ee_offs [nb+1] host int64."""
+        cfg = self.cfg
+        nb = len(ee_offs) - 1
+        dev = points.device
+        counts = (ee_offs[1:] - ee_offs[:-1]).numpy()
+        ok = np.nonzero(counts >= cfg.ee_point_counts_threshold)[0]
+        res = dict(ok_frames=ok, ee_pose=None, kp_pose=None, icp_stats=None, key_points=None)
+        if len(ok) == 0 or self.rot_model is None:
+            return res
+        # compact the crops of the frames that pass the gate
+        sel = torch.cat([ee_idx[int(ee_offs[f]):int(ee_offs[f + 1])] for f in ok])
+        S = len(ok)
+        seg_counts = counts[ok]
+        soffs = np.zeros(S + 1, dtype=np.int32)
+        np.cumsum(seg_counts, out=soffs[1:])
+        seg_ids = torch.repeat_interleave(torch.arange(S, device=dev), torch.as_tensor(seg_counts, device=dev))
+        pts = points[sel].contiguous()
+        feats = rgb_norm[sel].contiguous()
+        segf = seg_ids.float()
+
+        # --- rotation (app/inference_engine.py:437-457)
+        mn, mx = _segment_minmax(pts, seg_ids, S)
+        center = (mx + mn) / 2
+        rot_pts = pts - center[seg_ids] if cfg.rot_center_at_origin else pts
+        fld = _field(rot_pts, feats, segf, cfg.rot_scale, S)
+        rot_out = self.rot_model(fld.sparse())          # [S, 7|10]
+        quat = rot_out[:, 3:7].float().contiguous()     # W,X,Y,Z
+        # --- translation (app/inference_engine.py:459-489)
+        pos = out_utils.translation_magic_batched(pts, soffs, quat, cfg.translation_x_offset)
+        ee_pose = torch.cat((pos, quat.double()), dim=1)  # x,y,z,qw,qx,qy,qz
+        res["ee_pose"] = ee_pose.cpu().numpy()
+
+        # --- key points (ME branch, app/inference_engine.py:539-555) + Kabsch (:384-393)
+        kp_T = None
+        if self.kp_model is not None:
+            kp_pts = pts - center[seg_ids] if cfg.kp_center_at_origin else pts
+            kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
+            kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
+            bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
+            th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
+            K = bp.shape[1]
+            valid = bp > th                                     # [S,K]
+            nvalid = valid.sum(1)
+            # pack the selected (reference kp, predicted point) pairs to the front of each row
+            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+            ref = self.ref_kp.to(dev)[: K][order]               # [S,K,3]
+            tgt = pts[bi.long().clamp(min=0)].double()          # [S,K,3]
+            tgt = torch.gather(tgt, 1, order.unsqueeze(-1).expand(-1, -1, 3))
+            R, t = rigid_transform_3D_batched(ref.contiguous(), tgt.contiguous(), nvalid.to(torch.int32))
+            kp_T = torch.zeros((S, 4, 4), dtype=torch.float64, device=dev)
+            kp_T[:, :3, :3], kp_T[:, :3, 3], kp_T[:, 3, 3] = R, t, 1.0
+            res["key_points"] = (bp.cpu().numpy(), (bi - torch.as_tensor(soffs[:-1], device=dev).unsqueeze(1))
+                                 .cpu().numpy(), nvalid.cpu().numpy())
+            res["kp_valid"] = (nvalid >= 4).cpu().numpy()
+
+        # --- ICP refinement of both poses (app/inference_engine.py:358-362)
+        ee_T = _poses_to_matrices(ee_pose)
+        if cfg.icp_enabled and self.cad is not None:
+            inits = [ee_T] + ([kp_T] if kp_T is not None else [])
+            T_all, stats = icp_p2p_batched(self.cad, pts, soffs, inits[0])
+            ee_T, res["icp_stats"] = T_all, stats.cpu().numpy()
+            if kp_T is not None:
+                kp_T, kstats = icp_p2p_batched(self.cad, pts, soffs, inits[1])
+                res["kp_icp_stats"] = kstats.cpu().numpy()
+        res["ee_T"] = ee_T.cpu().numpy()
+        res["ee_pose"] = np.stack([get_pose_from_matrix(T) for T in res["ee_T"]])
+        if kp_T is not None:
+            res["kp_T"] = kp_T.cpu().numpy()
+            res["kp_pose"] = np.stack([get_pose_from_matrix(T) for T in res["kp_T"]])
+        return res
+
+    @torch.no_grad()
+    def predict_batch(self, frames, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None):
+        """frames: list of (points [N,3] f32, rgb [N,3] f32) host arrays. gt_labels: optional list of label arrays
+        used for the EE crop instead of the predicted labels (random-init weights give no usable EE)."""
+        dev = torch.device("cuda")
+        points, rgb, bidx, offs = batch_frames(frames, dev)
+        nb = len(frames)
+        rgbn = normalize_colors_(rgb)
+        labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
+        seg_labels = labels
+        if gt_labels is not None:
+            labels = torch.as_tensor(np.concatenate(gt_labels).astype(np.uint8)).to(dev)
+        labels2, ee_idx, ee_offs = self.filter_ee(points, labels.clone(), bidx, nb)
+        if gt_labels is None:
+            seg_labels = labels2
+        pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)
+        seg_h = seg_labels.cpu().numpy()
+        results = [FrameResult(segmentation=seg_h[offs[i]:offs[i + 1]]) for i in range(nb)]
+        for j, f in enumerate(pose["ok_frames"]):
+            r = results[f]
+            if pose.get("ee_pose") is not None:
+                r.ee_pose = pose["ee_pose"][j]
+            if pose.get("kp_pose") is not None and pose["kp_valid"][j]:
+                r.key_points_pose = pose["kp_pose"][j]
+            if pose.get("icp_stats") is not None:
+                r.icp_stats = pose["icp_stats"][j]
+            if ee2base_poses is not None and ee2base_poses[f] is not None:
+                if r.ee_pose is not None:
+                    r.base_pose = get_base2cam_pose(r.ee_pose, ee2base_poses[f])
+                if r.key_points_pose is not None:
+                    r.key_points_base_pose = get_base2cam_pose(r.key_points_pose, ee2base_poses[f])
+            r.is_confident = r.ee_pose is not None
+        return results
+
+
+def _poses_to_matrices(poses):
+    """[S,7] x,y,z,qw,qx,qy,qz (torch f64, device) -> [S,4,4] with the formula of utils/transformation.py:16-60."""
+    q0, q1, q2, q3 = poses[:, 3], poses[:, 4], poses[:, 5], poses[:, 6]
+    T = torch.zeros((poses.shape[0], 4, 4), dtype=torch.float64, device=poses.device)
+    T[:, 0, 0] = 2 * (q0 * q0 + q1 * q1) - 1
+    T[:, 0, 1] = 2 * (q1 * q2 - q0 * q3)
+    T[:, 0, 2] = 2 * (q1 * q3 + q0 * q2)
+    T[:, 1, 0] = 2 * (q1 * q2 + q0 * q3)
+    T[:, 1, 1] = 2 * (q0 * q0 + q2 * q2) - 1
+    T[:, 1, 2] = 2 * (q2 * q3 - q0 * q1)
+    T[:, 2, 0] = 2 * (q1 * q3 - q0 * q2)
+    T[:, 2, 1] = 2 * (q2 * q3 + q0 * q1)
+    T[:, 2, 2] = 2 * (q0 * q0 + q3 * q3) - 1
+    T[:, :3, 3] = poses[:, :3]
+    T[:, 3, 3] = 1.0
+    return T

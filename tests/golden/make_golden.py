@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz by IMPORTING the parts of the reference that run in the authoring container
+(utils/transformation.py, utils/calibration.py, utils/preprocess.py) and recording their
+outputs on seeded inputs. /root/reference does not exist on the GPU box, so the vectors are committed.
+
+    python tests/golden/make_golden.py        # needs /root/reference
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference_utils():
+    for name in ("ipdb", "turtle"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.pos = None
+            m.set_trace = lambda *a, **k: None
+            sys.modules[name] = m
+    sys.path.insert(0, REF)
+    from utils import transformation, preprocess  # noqa
+    from utils import calibration  # noqa
+    return transformation, calibration, preprocess
+
+
+def main():
+    T, Cal, P = import_reference_utils()
+    rng = np.random.default_rng(13)
+    out = {}
+
+    # ---- Kabsch: get_rigid_transform_3D (utils/transformation.py:178-222)
+    refs, tgts, Rs, ts, ns = [], [], [], [], []
+    kmax = 10
+    for case in range(64):
+        k = int(rng.integers(3, kmax + 1))
+        a = rng.normal(0, 0.08, (k, 3))
+        if case % 8 == 0:
+            a[:, 2] = 0.0                      # planar key points
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        Rg = T.get_quaternion_rotation_matrix(q, switch_w=False)
+        b = a @ Rg.T + rng.normal(0, 1.0, 3) + rng.normal(0, 0.002, (k, 3))
+        if case % 16 == 5:
+            b = b * np.array([1, 1, -1.0])     # mirrored target: exercises the reflection branch
+        R, t = T.get_rigid_transform_3D(a, b)
+        pa, pb = np.zeros((kmax, 3)), np.zeros((kmax, 3))
+        pa[:k], pb[:k] = a, b
+        refs.append(pa); tgts.append(pb); Rs.append(R); ts.append(t); ns.append(k)
+    out.update(kabsch_ref=np.array(refs), kabsch_tgt=np.array(tgts), kabsch_R=np.array(Rs), kabsch_t=np.array(ts),
+               kabsch_n=np.array(ns, dtype=np.int32))
+
+    # ---- quaternion / pose algebra
+    quats = rng.normal(size=(32, 4))
+    quats /= np.linalg.norm(quats, axis=1, keepdims=True)
+    poses = np.concatenate((rng.normal(0, 1, (32, 3)), quats), axis=1)
+    poses2 = np.concatenate((rng.normal(0, 1, (32, 3)), np.roll(quats, 5, axis=0)), axis=1)
+    out.update(
+        quat=quats,
+        quat_matrix=np.array([T.get_quaternion_rotation_matrix(q, switch_w=False) for q in quats]),
+        quat_matrix_switch=np.array([T.get_quaternion_rotation_matrix(np.roll(q, -1), switch_w=True) for q in quats]),
+        pose=poses, pose2=poses2,
+        pose_matrix=np.array([T.get_transformation_matrix(p, switch_w=False) for p in poses]),
+        pose_roundtrip=np.array([T.get_pose_from_matrix(T.get_transformation_matrix(p)) for p in poses]),
+        pose_inverse=np.array([T.get_pose_inverse(p) for p in poses]),
+        base2cam=np.array([T.get_base2cam_pose(p, p2) for p, p2 in zip(poses, poses2)]),
+        pose2pose=np.array([T.transform_pose2pose(p, p2) for p, p2 in zip(poses, poses2)]),
+        switch_w=np.array([T.switch_w(np.concatenate((p[:3], np.roll(p[3:], -1)))) for p in poses]),
+    )
+
+    # ---- calibration averaging (utils/calibration.py:69-139)
+    base = poses[0]
+    noisy = np.tile(base, (10, 1))
+    noisy[:, :3] += rng.normal(0, 0.01, (10, 3))
+    noisy[:, 3:] += rng.normal(0, 0.01, (10, 4))
+    noisy[:, 3:] /= np.linalg.norm(noisy[:, 3:], axis=1, keepdims=True)
+    w = rng.random(10) + 0.5
+    out.update(avg_in=noisy, avg_w=w, avg_out=Cal.compute_poses_average(noisy),
+               avg_out_w=Cal.compute_poses_average(noisy, weights=w),
+               outlier_in=np.concatenate((rng.normal(0, 1, 20), [15.0, -12.0])),
+               )
+    out["outlier_flags"] = Cal.get_outliers(out["outlier_in"])[0]
+
+    # ---- preprocess (utils/preprocess.py:8-37)
+    pts = rng.normal(0, 0.2, (500, 3)).astype(np.float32)
+    rgb255 = (rng.random((500, 3)) * 255).astype(np.float32)
+    rgb01 = rng.random((500, 3)).astype(np.float32)
+    c, off = P.center_at_origin(pts)
+    out.update(pre_pts=pts, pre_centered=c, pre_offset=off, pre_rgb255=rgb255, pre_rgb255_out=P.normalize_colors(rgb255),
+               pre_rgb01=rgb01, pre_rgb01_out=P.normalize_colors(rgb01))
+    np.savez_compressed(os.path.join(HERE, "reference_geometry.npz"), **out)
+
+    # ---- CAD input fixture: xyz of app/hand_files/hand.pcd (4480 points), read with our PCD reader
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "markerless-robot-camera-calibration_b200"))
+    from b200calib.icp import read_pcd_xyz
+    cad = read_pcd_xyz(os.path.join(REF, "app", "hand_files", "hand.pcd"))
+    np.savez_compressed(os.path.join(HERE, "cad_hand_points.npz"), xyz=cad.astype(np.float32))
+    print("kabsch cases", len(ns), "cad points", cad.shape, cad.min(0), cad.max(0))
+
+
+if __name__ == "__main__":
+    main()

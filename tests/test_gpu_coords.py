@@ -1,0 +1,135 @@
+"""K1-K3 parity (bit-exact): voxel coordinates, inverse maps, voxel features, stride maps, kernel maps."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.MinkowskiEngine as OME
+from gpu_util import kinect_like_cloud
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_me():
+    import MinkowskiEngine as ME
+    return ME
+
+
+def _fields(points_list, feats_list, scale):
+    ME = _cuda_me()
+    co = OME.utils.batched_coordinates([torch.from_numpy(p) * scale for p in points_list], dtype=torch.float32)
+    fe = torch.from_numpy(np.concatenate(feats_list))
+    of = OME.TensorField(features=fe, coordinates=co)
+    cf = ME.TensorField(features=fe, coordinates=co, device="cuda")
+    return of, cf
+
+
+@pytest.mark.parametrize("n,scale,batches", [(20000, 100.0, 1), (50000, 200.0, 3), (3000, 20.0, 2)])
+def test_voxelize_bit_exact(n, scale, batches):
+    pts = [kinect_like_cloud(n, 10 + b) - np.float32(b == 1) * 2 for b in range(batches)]  # batch 1 has negatives
+    feats = [np.random.default_rng(b).random((n, 3)).astype(np.float32) - 0.5 for b in range(batches)]
+    of, cf = _fields(pts, feats, scale)
+    os_, cs = of.sparse(), cf.sparse()
+    assert torch.equal(cs.C.cpu(), os_.C)                                   # coordinates, first-occurrence order
+    assert torch.equal(cf.inverse_mapping.cpu().long(), of.inverse_mapping)  # inverse map
+    assert torch.equal(cs.F.cpu(), os_.F)                                   # fixed-point mean: bit-exact features
+    assert torch.equal(cs.slice(cf).F.cpu(), os_.slice(of).F)
+
+
+def test_voxelize_edge_cases():
+    ME = _cuda_me()
+    # all points in one voxel; duplicates; a single point
+    for pts in (np.full((1000, 3), 0.3, np.float32), np.array([[-0.5, 0.2, 0.9]], np.float32),
+                np.repeat(np.array([[1.5, 2.5, 3.5], [-1.5, -2.5, -3.5]], np.float32), 7, axis=0)):
+        fe = torch.arange(len(pts) * 3, dtype=torch.float32).view(-1, 3) / 100
+        co = OME.utils.batched_coordinates([torch.from_numpy(pts)], dtype=torch.float32)
+        o = OME.TensorField(features=fe, coordinates=co).sparse()
+        c = ME.TensorField(features=fe, coordinates=co, device="cuda").sparse()
+        assert torch.equal(c.C.cpu(), o.C) and torch.equal(c.F.cpu(), o.F)
+    # exact voxel boundaries and negative zero
+    pts = np.array([[0.0, -0.0, 1.0], [-1.0, -1e-7, 0.999999], [2.0, 2.0, 2.0], [1.9999999, 2.0, 2.0]], np.float32)
+    co = OME.utils.batched_coordinates([torch.from_numpy(pts)], dtype=torch.float32)
+    fe = torch.ones(4, 1)
+    o = OME.TensorField(features=fe, coordinates=co).sparse()
+    c = ME.TensorField(features=fe, coordinates=co, device="cuda").sparse()
+    assert torch.equal(c.C.cpu(), o.C)
+    # out-of-range coordinate is an error, not a wrong answer
+    far = torch.tensor([[0.0, 2e5, 0.0, 0.0]])
+    with pytest.raises(ME.B2MEError):
+        ME.TensorField(features=torch.ones(1, 1), coordinates=far, device="cuda").sparse()
+
+
+def test_sparse_tensor_int_coords_first_wins():
+    ME = _cuda_me()
+    g = torch.Generator().manual_seed(0)
+    q = torch.randint(-6, 7, (5000, 3), generator=g)
+    co = OME.utils.batched_coordinates([q])
+    fe = torch.rand(5000, 4, generator=g)
+    o = OME.SparseTensor(fe, co)
+    c = ME.SparseTensor(fe, co, device="cuda")
+    assert torch.equal(c.C.cpu(), o.C) and torch.equal(c.F.cpu(), o.F)
+
+
+def test_stride_and_kernel_maps_bit_exact():
+    ME = _cuda_me()
+    pts = [kinect_like_cloud(40000, 21), kinect_like_cloud(30000, 22) - np.float32(1.0)]
+    feats = [np.zeros((len(p), 1), np.float32) for p in pts]
+    of, cf = _fields(pts, feats, 100.0)
+    os_, cs = of.sparse(), cf.sparse()
+    om, cm = os_.coordinate_manager, cs.coordinate_manager
+    ok, ck = os_.coordinate_map_key, cs.coordinate_map_key
+    for level in range(4):
+        nbr_o = om.kernel_map_k3(ok)
+        nbr_c = cm.kernel_map_k3(ck)
+        assert np.array_equal(nbr_c.cpu().numpy().astype(np.int64), nbr_o), f"k3 map, level {level}"
+        ok2, rec_o = om.stride_down(ok)
+        ck2, rec_c = cm.stride_down(ck)
+        assert np.array_equal(cm.coordinates(ck2).cpu().numpy(), om.levels[ok2].coords), f"stride coords {level}"
+        assert np.array_equal(rec_c["in2out"].cpu().numpy().astype(np.int64), rec_o["in2out"])
+        assert np.array_equal(rec_c["koff"].cpu().numpy().astype(np.int64), rec_o["koff"])
+        assert np.array_equal(rec_c["nbr_down"].cpu().numpy().astype(np.int64), rec_o["nbr_down"])
+        assert np.array_equal(rec_c["nbr_up"].cpu().numpy().astype(np.int64), rec_o["nbr_up"])
+        ok, ck = ok2, ck2
+    # kernel-map properties that hold at any size: centre = identity, symmetry nbr[nbr[o,k], 26-k] == o
+    nbr = cm.kernel_map_k3(cs.coordinate_map_key).long()
+    V = nbr.shape[0]
+    assert torch.equal(nbr[:, 13], torch.arange(V, device="cuda"))
+    for k in (0, 5, 12, 20):
+        rows = torch.nonzero(nbr[:, k] >= 0).flatten()
+        assert torch.equal(nbr[nbr[rows, k], 26 - k], rows)
+
+
+def test_sparse_quantize_matches_oracle():
+    ME = _cuda_me()
+    rng = np.random.default_rng(3)
+    pts = (rng.random((20000, 3)) * 2 - 1).astype(np.float32)
+    feats = rng.random((20000, 3)).astype(np.float32)
+    labels = rng.integers(0, 3, 20000).astype(np.int32)
+    a = OME.utils.sparse_quantize(pts, feats, labels, quantization_size=0.01, ignore_label=-100)
+    b = ME.utils.sparse_quantize(pts, feats, labels, quantization_size=0.01, ignore_label=-100)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    ia, va = OME.utils.sparse_quantize(pts, return_maps_only=True, return_inverse=True, quantization_size=0.05)
+    ib, vb = ME.utils.sparse_quantize(pts, return_maps_only=True, return_inverse=True, quantization_size=0.05)
+    assert np.array_equal(ia, ib) and np.array_equal(va, vb)
+
+
+def test_full_size_properties():
+    """BASELINE config-2 frame size (~300k points, 5 mm voxels): size-independent properties."""
+    ME = _cuda_me()
+    from b200calib.synthetic import make_frame
+    f = make_frame(13)
+    pts = torch.from_numpy(f["points"])
+    co = OME.utils.batched_coordinates([pts * 200.0], dtype=torch.float32)
+    fld = ME.TensorField(features=torch.from_numpy(f["rgb"]) - 0.5, coordinates=co, device="cuda")
+    st = fld.sparse()
+    C, inv = st.C, fld.inverse_mapping.long()
+    assert torch.equal(C[inv][:, 1:], torch.floor(co[:, 1:].cuda()).int())           # every point lands in its voxel
+    assert torch.unique(C, dim=0).shape[0] == C.shape[0]                             # rows are unique
+    first = torch.full((C.shape[0],), 1 << 40, dtype=torch.long, device="cuda")
+    first.scatter_reduce_(0, inv, torch.arange(len(inv), device="cuda"), reduce="amin")
+    assert bool((first[1:] > first[:-1]).all())                                       # first-occurrence order
+    cnt = torch.bincount(inv, minlength=C.shape[0])
+    mean = torch.zeros_like(st.F, dtype=torch.float64).index_add_(0, inv, fld.F.double()) / cnt.unsqueeze(1)
+    assert torch.allclose(st.F.double(), mean, atol=1e-6)
+    st2 = ME.TensorField(features=fld.F, coordinates=co, device="cuda").sparse()      # idempotent / deterministic
+    assert torch.equal(st2.C, C) and torch.equal(st2.F, st.F)

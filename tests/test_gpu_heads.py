@@ -1,0 +1,92 @@
+"""K5-K8 parity: pooling, key-point / vote reductions, translation, largest EE cluster vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.MinkowskiEngine as OME
+from oracle import geometry as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_largest_cluster_matches_oracle_and_sklearn():
+    from b200calib import output as O
+    rng = np.random.default_rng(0)
+    segs = []
+    for s in range(5):
+        blobs = [rng.normal(rng.uniform(-0.5, 0.5, 3), 0.03, (int(rng.integers(50, 900)), 3)) for _ in range(4)]
+        segs.append(np.concatenate(blobs).astype(np.float32))
+    segs.append(rng.random((3, 3)).astype(np.float32) * 5)      # tiny segment, all isolated
+    segs.append(np.zeros((0, 3), np.float32))                   # empty segment
+    offs = np.zeros(len(segs) + 1, np.int32)
+    offs[1:] = np.cumsum([len(s) for s in segs])
+    allp = torch.from_numpy(np.concatenate(segs)).cuda()
+    mask, sizes = O.largest_cluster_mask(allp, offs, 0.06)
+    mask = mask.cpu().numpy().astype(bool)
+    for s, p in enumerate(segs):
+        got = np.nonzero(mask[offs[s]:offs[s + 1]])[0]
+        want = G.largest_cluster(p, 0.06)
+        assert np.array_equal(got, np.sort(want)), f"segment {s}"
+        assert int(sizes[s]) == len(want)
+        if 10 < len(p) < 3000:
+            assert np.array_equal(got, np.sort(G.largest_cluster_sklearn(p, 0.06)))
+    idx = O.ClusterUtil().get_largest_cluster(segs[0])
+    assert np.array_equal(idx, np.sort(G.largest_cluster(segs[0])))
+
+
+def test_keypoint_vote_translation():
+    from b200calib import output as O
+    g = torch.Generator().manual_seed(1)
+    sizes = [700, 2048, 1, 0, 333]
+    offs = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    n = int(offs[-1])
+    logits = torch.randn(n, 6, generator=g) * 3
+    pts = torch.rand(n, 3, generator=g)
+    bp, bi = O.key_point_predictions_batched(logits.cuda(), offs)
+    vc = O.vote_centers_batched(logits.cuda(), pts.cuda(), offs, col=1, topk=8)
+    quat = torch.nn.functional.normalize(torch.randn(len(sizes), 4, generator=g), dim=1)
+    tr = O.translation_magic_batched(pts.cuda(), offs, quat.cuda())
+    for s in range(len(sizes)):
+        a, b = offs[s], offs[s + 1]
+        if b == a:
+            continue
+        p, i = G.key_point_best(logits[a:b])
+        assert np.allclose(bp[s].cpu().numpy(), p, atol=2e-6)
+        same = (bi[s].cpu().numpy() - a) == i
+        # a different row may only win when its probability is within rounding of the best
+        probs = torch.softmax(logits[a:b], 1).numpy()
+        for c in np.nonzero(~same)[0]:
+            assert abs(probs[bi[s, c].item() - a, c] - p[c]) < 2e-6
+        want = G.pred_center(logits[a:b], pts[a:b].numpy())
+        assert np.allclose(vc[s].cpu().numpy(), want, atol=1e-6)
+        wt = G.translation_magic(pts[a:b].numpy(), quat[s].numpy())
+        assert np.allclose(tr[s].cpu().numpy(), wt, atol=1e-5)     # tolerance 1e-4 m (north star); fp32 inside
+    idx, classes, probs = O.get_key_point_predictions(logits[:700], conf_th=0.5)
+    oi, oc, op = G.key_point_predictions(logits[:700], conf_th=0.5)
+    assert np.array_equal(classes, oc) and np.array_equal(idx, oi)
+
+
+def test_global_pool_and_slice():
+    import MinkowskiEngine as ME
+    g = torch.Generator().manual_seed(2)
+    pts = [torch.rand(n, 3, generator=g) * 30 for n in (4000, 10, 2500)]
+    fe = torch.randn(6510, 16, generator=g)
+    co = OME.utils.batched_coordinates(pts, dtype=torch.float32)
+    o = OME.TensorField(features=fe, coordinates=co).sparse()
+    c = ME.TensorField(features=fe, coordinates=co, device="cuda").sparse()
+    for mod in ("MinkowskiGlobalAvgPooling", "MinkowskiGlobalMaxPooling"):
+        po = getattr(OME, mod)()(o).F
+        pc = getattr(ME, mod)()(c).F.cpu()
+        assert po.shape == pc.shape == (3, 16)
+        assert torch.allclose(pc, po, atol=1e-5)
+    bn = ME.MinkowskiBatchNorm(16).cuda().eval()
+    obn = OME.MinkowskiBatchNorm(16).eval()
+    with torch.no_grad():
+        bn.bn.running_mean.normal_(); bn.bn.running_var.uniform_(0.5, 2); bn.bn.weight.normal_(); bn.bn.bias.normal_()
+    obn.load_state_dict({k: v.cpu() for k, v in bn.state_dict().items()})
+    relu_c, relu_o = ME.MinkowskiLeakyReLU(), OME.MinkowskiLeakyReLU()
+    with torch.no_grad():
+        yc = relu_c(bn(c)) + c          # stand-alone affine+act kernel, then an un-fused add
+        yo = relu_o(obn(o)) + o
+    assert torch.allclose(yc.F.cpu(), yo.F, atol=1e-5)
+    assert torch.allclose(ME.cat(yc, c).F.cpu(), OME.cat(yo, o).F, atol=1e-5)

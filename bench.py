@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — segmented-and-posed frames/s of the markerless-calibration inference hot path on B200.
+
+One "step" = one pass of the whole per-batch pipeline over `--frames` synthetic 640x480 Kinect-shaped frames per
+GPU (BASELINE.json configs[1] + [2]): voxelise (K1) -> kernel maps (K2/K3) -> MinkUNet18D segmentation forward in
+bf16 on tcgen05 (K4) -> head + per-point arg-max (K5) -> largest EE cluster (K7) -> RobotNetEncode rotation (K1-K4,
+K6) -> "magic" translation -> key-point network + per-class reduction (K8) -> batched Kabsch (K9) -> ICP x2 (K10).
+Random-init weights of the named architectures, synthetic data (dataset and checkpoints are unpublished).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (under torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            # CPU oracle of the reference path on the host cores
+
+Prints ONE JSON line (rank 0). `value` = frames/s with inputs resident in HBM; `e2e` = the same through the public
+API with pinned host buffers (H2D of the inputs, D2H of labels and poses inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "markerless-robot-camera-calibration_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+SEED = 13  # TEST.seed of config/default.yaml:112
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step (batch)")
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--scale", type=float, default=200.0, help="voxels per metre (200 = 5 mm, production)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-icp", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    return ap.parse_args()
+
+
+def _gen_frame(a):
+    from b200calib.synthetic import make_frame
+    seed, w, h = a
+    f = make_frame(seed, width=w, height=h)
+    return f["points"], f["rgb"], f["labels"].astype(np.uint8)
+
+
+def make_workload(n_frames, rank, width, height):
+    """n_frames distinct seeded frames for this rank (generated before CUDA is touched, in worker processes)."""
+    import multiprocessing as mp
+    seeds = [(SEED * 1000 + rank * 4096 + i, width, height) for i in range(n_frames)]
+    nproc = max(1, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    if nproc > 1 and n_frames > 1:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            return pool.map(_gen_frame, seeds)
+    return [_gen_frame(s) for s in seeds]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained",
+                                                                                 d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_models(ME, kp_classes=6):
+    import torch
+    from b200calib.models import make_models, randomize_bn_stats
+    torch.manual_seed(SEED)
+    M = make_models(ME)
+    seg = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=3), SEED).eval()
+    rot = randomize_bn_stats(M.RobotNetEncode(3, 7), SEED + 1).eval()
+    kp = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=kp_classes), SEED + 2).eval()
+    return seg, rot, kp
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """the reference's own per-frame CPU path, restated (oracle/pipeline.py; the real one needs MinkowskiEngine 0.5.4
+    + Open3D, absent here), on all host threads. Each step = ONE frame of the workload (a bounded sample)."""
+    if rank != 0:
+        return
+    import torch
+    import oracle.MinkowskiEngine as OME
+    from oracle import pipeline as op
+    from b200calib.synthetic import ee_surface_cloud
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    seg, rot, kp = build_models(OME)
+    nfr = min(args.frames, args.warmup + args.steps)
+    frames = make_workload(max(1, min(nfr, 2)), 0, args.width, args.height)
+    cad = ee_surface_cloud(4096, SEED)
+    cfg = dict(seg_scale=args.scale, icp_enabled=not args.no_icp)
+    models = dict(seg=seg, rot=rot, kp=kp)
+
+    def one(i):
+        p, c, l = frames[i % len(frames)]
+        return op.predict_frame(models, cad, p, c, cfg, gt_labels=l)
+
+    for i in range(min(args.warmup, 1)):  # one warm-up frame is ~30 s of CPU work; more would not change the number
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = f"{args.steps} frames, one 640x480 frame per step, batch 1 fp32 (the reference's mode)"
+    print(json.dumps({
+        "impl": "reference", "metric": "segmented-and-posed frames/s", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": (f"segmentation forward (MinkUNet18D, 3 classes) + EE pose (RobotNetEncode rotation, magic "
+                         f"translation, 6-key-point MinkUNet18D + Kabsch, ICP x2) on {args.frames} synthetic "
+                         f"{args.width}x{args.height} Kinect-shaped frames per GPU, voxel {1.0 / args.scale * 1000:.1f} mm "
+                         f"(seg/rot), 1.25 mm (key points); BASELINE.json configs[1]+[2]"),
+            "frames_per_gpu": args.frames, "points_per_frame": "~3.0e5", "voxel_m": 1.0 / args.scale,
+            "ee_crop": "ground-truth labels (random-init weights give no usable EE prediction)",
+            "l2": "inputs and activations exceed L2 (126 MB) every step; no explicit flush",
+            "parallelism": "frames sharded across GPUs, one final all_gather of pose records"}
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, world, local):
+    frames = make_workload(args.frames, rank, args.width, args.height)   # before CUDA init (fork pool)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (B200 arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import MinkowskiEngine as ME
+    from b200calib import dist as bdist
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig
+    from b200calib.synthetic import ee_surface_cloud
+    bdist.init_from_env("nccl" if world > 1 else None)
+    ME.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
+    seg, rot, kp = [m.to(dev) for m in build_models(ME)]
+    cad = torch.from_numpy(ee_surface_cloud(4096, SEED)).to(dev)
+    cfg = PipelineConfig(seg_scale=args.scale, icp_enabled=not args.no_icp)
+    eng = BatchedInferenceEngine(seg, rot, kp, cad_points=cad, config=cfg)
+
+    # pinned host staging of this rank's batch (the "host buffers" of the e2e number)
+    counts = [len(f[0]) for f in frames]
+    offs = np.zeros(len(frames) + 1, dtype=np.int64)
+    np.cumsum(counts, out=offs[1:])
+    N = int(offs[-1])
+    h_pts = torch.from_numpy(np.concatenate([f[0] for f in frames])).pin_memory()
+    h_rgb = torch.from_numpy(np.concatenate([f[1] for f in frames])).pin_memory()
+    h_bidx = torch.from_numpy(np.repeat(np.arange(len(frames), dtype=np.float32), counts)).pin_memory()
+    h_lab = torch.from_numpy(np.concatenate([f[2] for f in frames])).pin_memory()
+    h_seg = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    d_pts, d_rgb, d_bidx, d_lab = [t.to(dev) for t in (h_pts, h_rgb, h_bidx, h_lab)]
+    torch.cuda.synchronize()
+
+    def step_device():
+        return eng.predict_device(d_pts, d_rgb, d_bidx, offs, gt_labels=d_lab)
+
+    def step_e2e():
+        p = h_pts.to(dev, non_blocking=True)
+        c = h_rgb.to(dev, non_blocking=True)
+        b = h_bidx.to(dev, non_blocking=True)
+        g = h_lab.to(dev, non_blocking=True)
+        labels, pose = eng.predict_device(p, c, b, offs, gt_labels=g)
+        h_seg.copy_(labels, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return eng.assemble(h_seg.numpy(), offs, pose)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also: census of the algorithmic work of every convolution launch, once)
+    recs_census = ME.set_profile("census")
+    step_device()
+    ME.set_profile(None)
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+    barrier()
+
+    # ---- timed: device-resident
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    recs_ev = ME.set_profile("events")
+    ME.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        labels, pose = step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = ME.launch_count()
+    ME.set_profile(None)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed: end to end through the public API with pinned host buffers
+    step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        results = step_e2e()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    posed = sum(1 for r in results if r.ee_pose is not None)
+
+    # ---- the only collective: all-gather of the per-frame records (outside the per-step loop, as in production)
+    recs = bdist.pack_records(list(range(rank * args.frames, (rank + 1) * args.frames)), results)
+    allrec = bdist.gather_records(recs)
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+
+    # ---- roofline of the dominant kernel (k_spconv_tc): FLOPs from the census / CUDA-event durations
+    per_step = len(recs_census)
+    tc_flops = tc_ms = simt_ms = 0.0
+    all_ms = 0.0
+    n_tc = 0
+    torch.cuda.synchronize()
+    for i, ev in enumerate(recs_ev):
+        c = recs_census[i % per_step]
+        ms = ev[0].elapsed_time(ev[1])
+        all_ms += ms
+        if c["kind"] == "tc":
+            tc_flops += 2.0 * c["pairs"] * c["Cin"] * c["Cout"]
+            tc_ms += ms
+            n_tc += 1
+        else:
+            simt_ms += ms
+    peaks = load_peaks()
+    roof = None
+    if tc_ms > 0:
+        ach = tc_flops / (tc_ms * 1e-3) / 1e12
+        roof = {"kernel": "k_spconv_tc (tcgen05 gather-GEMM sparse convolution)", "bound": "tensor", "achieved": ach,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "peak_source": f"{peaks['src']} bf16 sustained (burst {peaks['tf_burst']})",
+                "launches_per_step": n_tc // max(args.steps, 1),
+                "share_of_step": tc_ms / ms_dev if world == 1 else None,
+                "simt_conv_share_of_step": simt_ms / ms_dev if world == 1 else None,
+                "flops_per_step": tc_flops / max(args.steps, 1)}
+
+    if rank != 0:
+        return
+    total_frames = args.frames * world
+    out = {
+        "metric": "segmented-and-posed frames/s", "value": total_frames * args.steps / (ms_dev * 1e-3),
+        "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": int(N * (12 + 12 + 4 + 1)), "d2h_bytes_per_step": int(N + posed * 20 * 8),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "frames_posed_per_step": int(posed) if world == 1 else int(np.nansum(allrec[:, 1])),
+        "points_per_step": N,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, frames)
+    print(json.dumps(out))
+
+
+def cpu_baseline(args, frames):
+    """oracle (CPU restatement of the reference path) on ONE frame of the same workload, all host threads."""
+    import torch
+    import oracle.MinkowskiEngine as OME
+    from oracle import pipeline as op
+    from b200calib.synthetic import ee_surface_cloud
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    seg, rot, kp = build_models(OME)
+    cad = ee_surface_cloud(4096, SEED)
+    p, c, l = frames[0]
+    t0 = time.perf_counter()
+    op.predict_frame(dict(seg=seg, rot=rot, kp=kp), cad, p, c, dict(seg_scale=args.scale,
+                                                                     icp_enabled=not args.no_icp), gt_labels=l)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 frame of the batch ({len(p)} points), batch 1 fp32, no warm-up, {dt:.1f} s"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from MinkowskiEngine._lib import lib, check, ptr, stream
+from MinkowskiEngine.core import _count
 from .transformation import get_transformation_matrix, get_pose_from_matrix
 
 ICP_THRESHOLD = 0.1      # utils/icp.py:42
@@ -88,6 +89,7 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
     check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
                                    ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")
+    _count(2)
     return out_T.view(F, 4, 4), stats
 
 

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from MinkowskiEngine._lib import lib, check, ptr, stream, B2MEError
+from MinkowskiEngine.core import _count
 
 
 def _offsets(seg_offsets, device):
@@ -35,6 +36,7 @@ def largest_cluster_mask(points, seg_offsets, dist=0.06):
         ws = torch.empty((lib.b2me_cluster_workspace_bytes(r1 - r0, s1 - s0),), dtype=torch.uint8, device=dev)
         check(lib.b2me_largest_cluster(ptr(points[r0:r1]), ptr(sub), s1 - s0, r1 - r0, float(dist), ptr(mask[r0:]),
                                        ptr(sizes[s0:]), ptr(ws), ws.numel(), stream()), "largest_cluster")
+        _count(18)  # cells (1) + unique (7) + count, scan x3, fill (5) + link, flatten, root, best, mask (5)
     return mask[:n], sizes[:S]
 
 
@@ -64,6 +66,7 @@ def key_point_predictions_batched(logits, seg_offsets):
     bp = torch.empty((S, K), dtype=torch.float32, device=dev)
     bi = torch.empty((S, K), dtype=torch.int32, device=dev)
     check(lib.b2me_keypoint_reduce(ptr(logits), K, ptr(offs), S, ptr(bp), ptr(bi), stream()), "keypoint_reduce")
+    _count(1)
     return bp, bi
 
 
@@ -86,6 +89,7 @@ def vote_centers_batched(logits, points, seg_offsets, col=1, topk=8):
     out = torch.empty((S, 3), dtype=torch.float32, device=dev)
     check(lib.b2me_vote_center(ptr(logits), logits.shape[1], col, ptr(points), ptr(offs), S, topk, ptr(out), stream()),
           "vote_center")
+    _count(1)
     return out
 
 
@@ -113,4 +117,5 @@ def translation_magic_batched(points, seg_offsets, quats_wxyz, x_offset=-0.015):
     out = torch.empty((S, 3), dtype=torch.float64, device=dev)
     check(lib.b2me_translation_magic(ptr(points), ptr(offs), S, ptr(q), float(x_offset), ptr(out), stream()),
           "translation_magic")
+    _count(1)
     return out

@@ -25,6 +25,7 @@ import torch
 
 import MinkowskiEngine as ME
 from MinkowskiEngine._lib import lib, check, ptr, stream
+from MinkowskiEngine.core import _count
 
 from . import output as out_utils
 from .icp import icp_p2p_batched
@@ -109,9 +110,11 @@ def segment_points(model, points, rgb, bidx, nb, scale):
     # slice + arg-max fused: arg-max per voxel, then 1 byte per point through the inverse map
     check(lib.b2me_linear_small(ptr(logits), 0, V, C, ptr(_eye(C, logits.device)), None, C, None, ptr(vlab), stream()),
           "argmax")
+    _count(1)
     N = points.shape[0]
     labels = torch.empty((max(N, 1),), dtype=torch.uint8, device=logits.device)
     check(lib.b2me_gather_labels(ptr(vlab), ptr(fld.inverse_mapping), N, ptr(labels), stream()), "gather_labels")
+    _count(1)
     return labels[:N], fld, out
 
 
@@ -245,22 +248,39 @@ class BatchedInferenceEngine:
         return res
 
     @torch.no_grad()
+    def predict_device(self, points, rgb, bidx, offs, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None):
+        """the whole per-batch pipeline on tensors that are already resident on the device.
+        points/rgb [N,3] f32, bidx [N] f32 frame index, offs [nb+1] host frame offsets; gt_labels: optional
+        [N] uint8 device tensor used for the EE crop instead of the predicted labels (random-init weights give no
+        usable EE). Returns (per-point labels uint8 on the device, pose dict on the host)."""
+        nb = len(offs) - 1
+        rgbn = normalize_colors_(rgb)
+        labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
+        seg_labels = labels
+        crop_src = labels if gt_labels is None else gt_labels
+        labels2, ee_idx, ee_offs = self.filter_ee(points, crop_src.clone(), bidx, nb)
+        if gt_labels is None:
+            seg_labels = labels2
+        pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)
+        pose["ee_counts"] = (ee_offs[1:] - ee_offs[:-1]).numpy()
+        return seg_labels, pose
+
+    @torch.no_grad()
     def predict_batch(self, frames, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None):
         """frames: list of (points [N,3] f32, rgb [N,3] f32) host arrays. gt_labels: optional list of label arrays
         used for the EE crop instead of the predicted labels (random-init weights give no usable EE)."""
         dev = torch.device("cuda")
         points, rgb, bidx, offs = batch_frames(frames, dev)
-        nb = len(frames)
-        rgbn = normalize_colors_(rgb)
-        labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
-        seg_labels = labels
+        gl = None
         if gt_labels is not None:
-            labels = torch.as_tensor(np.concatenate(gt_labels).astype(np.uint8)).to(dev)
-        labels2, ee_idx, ee_offs = self.filter_ee(points, labels.clone(), bidx, nb)
-        if gt_labels is None:
-            seg_labels = labels2
-        pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)
-        seg_h = seg_labels.cpu().numpy()
+            gl = torch.as_tensor(np.concatenate(gt_labels).astype(np.uint8)).to(dev)
+        seg_labels, pose = self.predict_device(points, rgb, bidx, offs, ee2base_poses, gl, kp_conf_threshold)
+        return self.assemble(seg_labels.cpu().numpy(), offs, pose, ee2base_poses)
+
+    @staticmethod
+    def assemble(seg_h, offs, pose, ee2base_poses=None):
+        """host-side ResultDTO assembly (app/inference_engine.py:288-369)."""
+        nb = len(offs) - 1
         results = [FrameResult(segmentation=seg_h[offs[i]:offs[i + 1]]) for i in range(nb)]
         for j, f in enumerate(pose["ok_frames"]):
             r = results[f]

@@ -10,6 +10,7 @@ import torch
 from scipy.spatial.transform import Rotation
 
 from MinkowskiEngine._lib import lib, check, ptr, stream
+from MinkowskiEngine.core import _count
 
 
 def switch_w(pose):
@@ -89,6 +90,7 @@ def rigid_transform_3D_batched(reference, target, npairs=None):
     t = torch.empty((P, 3), dtype=torch.float64, device=dev)
     check(lib.b2me_kabsch_batched(ptr(reference), ptr(target), ptr(npairs), P, kmax, ptr(R), ptr(t), stream()),
           "kabsch_batched")
+    _count(1)
     return R.view(P, 3, 3), t
 
 

@@ -423,7 +423,8 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
                                     double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* out_T,
                                     double* out_stats, void* ws, size_t ws_bytes, b2me_stream_t stream) {
-    if (!source_xyz || !target_xyz || !tgt_offsets || !init_T || !out_T || !out_stats || !ws) return B2ME_EINVAL;
+    if (!source_xyz || !tgt_offsets || !init_T || !out_T || !out_stats || !ws) return B2ME_EINVAL;
+    if (!target_xyz && T_total > 0) return B2ME_EINVAL;  // an empty target cloud may come with a null pointer
     if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
     if (F == 0) return B2ME_OK;
     IcpWs w = carve_icp_ws(ws, T_total, F);

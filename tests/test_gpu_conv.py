@@ -153,12 +153,13 @@ def test_linear_small_and_gathers():
     x = torch.randn(V, 1024, generator=g)
     lin = torch.nn.Linear(1024, 3)
     ref = lin(x).detach()
+    Wc, bc = lin.weight.detach().cuda().contiguous(), lin.bias.detach().cuda()   # keep alive across the launch
     for xin in (x, x.bfloat16()):
         out = torch.empty((V, 3), device="cuda")
         am = torch.empty((V,), dtype=torch.uint8, device="cuda")
         xc = xin.cuda()
         check(lib.b2me_linear_small(ptr(xc), 0 if xin.dtype == torch.float32 else 1, V, 1024,
-                                    ptr(lin.weight.detach().cuda().contiguous()), ptr(lin.bias.detach().cuda()), 3,
+                                    ptr(Wc), ptr(bc), 3,
                                     ptr(out), ptr(am), stream()))
         r = lin(xin.float()).detach()
         assert rel_err(out, r) < 1e-5
@@ -167,5 +168,6 @@ def test_linear_small_and_gathers():
     inv = torch.randint(0, V, (20000,), generator=g).int()
     lab = torch.randint(0, 3, (V,), generator=g).to(torch.uint8)
     outl = torch.empty((20000,), dtype=torch.uint8, device="cuda")
-    check(lib.b2me_gather_labels(ptr(lab.cuda()), ptr(inv.cuda()), 20000, ptr(outl), stream()))
+    labc, invc = lab.cuda(), inv.cuda()
+    check(lib.b2me_gather_labels(ptr(labc), ptr(invc), 20000, ptr(outl), stream()))
     assert torch.equal(outl.cpu(), lab[inv.long()])

@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--scale", type=float, default=200.0, help="voxels per metre (200 = 5 mm, production)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-icp", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="one extra (untimed) step with synchronised per-stage times")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     return ap.parse_args()
 
 
@@ -272,6 +274,13 @@ def run_b200(args, rank, world, local):
     ms_e2e = e2.elapsed_time(e3)
     posed = sum(1 for r in results if r.ee_pose is not None)
 
+    stage_ms = None
+    if args.stages:
+        eng.stage_times = {}
+        step_device()
+        stage_ms = {k: round(v, 3) for k, v in eng.stage_times.items()}
+        eng.stage_times = None
+
     # ---- the only collective: all-gather of the per-frame records (outside the per-step loop, as in production)
     recs = bdist.pack_records(list(range(rank * args.frames, (rank + 1) * args.frames)), results)
     allrec = bdist.gather_records(recs)
@@ -296,6 +305,16 @@ def run_b200(args, rank, world, local):
             n_tc += 1
         else:
             simt_ms += ms
+    if args.conv_table and rank == 0:
+        tab = []
+        for i in range(per_step):
+            c = dict(recs_census[i])
+            ms = [recs_ev[j][0].elapsed_time(recs_ev[j][1]) for j in range(i, len(recs_ev), per_step)]
+            c["ms"] = float(np.mean(ms))
+            c["tflops"] = 2.0 * c["pairs"] * c["Cin"] * c["Cout"] / (c["ms"] * 1e-3) / 1e12
+            c["fill"] = c["pairs"] / max(1, c["K"] * c["V_out"])
+            tab.append(c)
+        json.dump(tab, open(args.conv_table, "w"))
     peaks = load_peaks()
     roof = None
     if tc_ms > 0:
@@ -323,6 +342,8 @@ def run_b200(args, rank, world, local):
         "frames_posed_per_step": int(posed) if world == 1 else int(np.nansum(allrec[:, 1])),
         "points_per_step": N,
     }
+    if stage_ms is not None:
+        out["stage_ms"] = stage_ms
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, frames)
     print(json.dumps(out))

@@ -17,6 +17,7 @@ Open3D ICP) in between. Here a batch of frames goes through every stage on the d
 
 Frames are independent, so multi-GPU runs shard frames across ranks (dist.py) and all-gather the poses.
 """
+import time
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -137,7 +138,27 @@ def _segment_minmax(points, seg_ids, S):
     return mn, mx
 
 
+class _Stage:
+    """opt-in per-stage wall times (device-synchronised on both sides); used by bench.py --stages only."""
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.stage_times is not None:
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if self.eng.stage_times is not None:
+            torch.cuda.synchronize()
+            d = self.eng.stage_times
+            d[self.name] = d.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+
+
 class BatchedInferenceEngine:
+    stage_times = None  # dict name -> ms when enabled
+
     def __init__(self, seg_model, rot_model=None, kp_model=None, cad_points=None, config=None,
                  reference_key_points=REFERENCE_KEY_POINTS):
         self.seg_model = seg_model.eval()
@@ -197,54 +218,82 @@ class BatchedInferenceEngine:
         segf = seg_ids.float()
 
         # --- rotation (app/inference_engine.py:437-457)
-        mn, mx = _segment_minmax(pts, seg_ids, S)
-        center = (mx + mn) / 2
-        rot_pts = pts - center[seg_ids] if cfg.rot_center_at_origin else pts
-        fld = _field(rot_pts, feats, segf, cfg.rot_scale, S)
-        rot_out = self.rot_model(fld.sparse())          # [S, 7|10]
-        quat = rot_out[:, 3:7].float().contiguous()     # W,X,Y,Z
+        with _Stage(self, "rotation"):
+            mn, mx = _segment_minmax(pts, seg_ids, S)
+            center = (mx + mn) / 2
+            rot_pts = pts - center[seg_ids] if cfg.rot_center_at_origin else pts
+            fld = _field(rot_pts, feats, segf, cfg.rot_scale, S)
+            rot_out = self.rot_model(fld.sparse())          # [S, 7|10]
+            quat = rot_out[:, 3:7].float().contiguous()     # W,X,Y,Z
         # --- translation (app/inference_engine.py:459-489)
-        pos = out_utils.translation_magic_batched(pts, soffs, quat, cfg.translation_x_offset)
-        ee_pose = torch.cat((pos, quat.double()), dim=1)  # x,y,z,qw,qx,qy,qz
-        res["ee_pose"] = ee_pose.cpu().numpy()
+        with _Stage(self, "translation"):
+            pos = out_utils.translation_magic_batched(pts, soffs, quat, cfg.translation_x_offset)
+            ee_pose = torch.cat((pos, quat.double()), dim=1)  # x,y,z,qw,qx,qy,qz
 
         # --- key points (ME branch, app/inference_engine.py:539-555) + Kabsch (:384-393)
         kp_T = None
         if self.kp_model is not None:
-            kp_pts = pts - center[seg_ids] if cfg.kp_center_at_origin else pts
-            kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
-            kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
-            bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
-            th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
-            K = bp.shape[1]
-            valid = bp > th                                     # [S,K]
-            nvalid = valid.sum(1)
-            # pack the selected (reference kp, predicted point) pairs to the front of each row
-            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
-            ref = self.ref_kp.to(dev)[: K][order]               # [S,K,3]
-            tgt = pts[bi.long().clamp(min=0)].double()          # [S,K,3]
-            tgt = torch.gather(tgt, 1, order.unsqueeze(-1).expand(-1, -1, 3))
-            R, t = rigid_transform_3D_batched(ref.contiguous(), tgt.contiguous(), nvalid.to(torch.int32))
-            kp_T = torch.zeros((S, 4, 4), dtype=torch.float64, device=dev)
-            kp_T[:, :3, :3], kp_T[:, :3, 3], kp_T[:, 3, 3] = R, t, 1.0
-            res["key_points"] = (bp.cpu().numpy(), (bi - torch.as_tensor(soffs[:-1], device=dev).unsqueeze(1))
-                                 .cpu().numpy(), nvalid.cpu().numpy())
-            res["kp_valid"] = (nvalid >= 4).cpu().numpy()
+            with _Stage(self, "key_points"):
+                kp_pts = pts - center[seg_ids] if cfg.kp_center_at_origin else pts
+                kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
+                kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
+                bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
+                th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
+                K = bp.shape[1]
+                valid = bp > th                                     # [S,K]
+                nvalid = valid.sum(1)
+                # pack the selected (reference kp, predicted point) pairs to the front of each row
+                order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+                ref = self.ref_kp.to(dev)[: K][order]               # [S,K,3]
+                tgt = pts[bi.long().clamp(min=0)].double()          # [S,K,3]
+                tgt = torch.gather(tgt, 1, order.unsqueeze(-1).expand(-1, -1, 3))
+                R, t = rigid_transform_3D_batched(ref.contiguous(), tgt.contiguous(), nvalid.to(torch.int32))
+                kp_T = torch.zeros((S, 4, 4), dtype=torch.float64, device=dev)
+                kp_T[:, :3, :3], kp_T[:, :3, 3], kp_T[:, 3, 3] = R, t, 1.0
+                res["key_points"] = (bp, bi - torch.as_tensor(soffs[:-1], device=dev).unsqueeze(1), nvalid)
+                kp_ok = nvalid >= 4
 
-        # --- ICP refinement of both poses (app/inference_engine.py:358-362)
-        ee_T = _poses_to_matrices(ee_pose)
-        if cfg.icp_enabled and self.cad is not None:
-            inits = [ee_T] + ([kp_T] if kp_T is not None else [])
-            T_all, stats = icp_p2p_batched(self.cad, pts, soffs, inits[0])
-            ee_T, res["icp_stats"] = T_all, stats.cpu().numpy()
+        # --- ICP refinement of both poses (app/inference_engine.py:358-362): ONE launch, 2S problems
+        with _Stage(self, "icp"):
+            ee_T = _poses_to_matrices(ee_pose)
+            stats = kstats = None
+            if cfg.icp_enabled and self.cad is not None:
+                if kp_T is not None:
+                    both_T = torch.cat((ee_T, kp_T))
+                    both_pts = torch.cat((pts, pts))
+                    both_offs = np.concatenate((soffs, soffs[1:] + soffs[-1])).astype(np.int32)
+                    T_all, st = icp_p2p_batched(self.cad, both_pts, both_offs, both_T)
+                    ee_T, kp_T, stats, kstats = T_all[:S], T_all[S:], st[:S], st[S:]
+                else:
+                    ee_T, stats = icp_p2p_batched(self.cad, pts, soffs, ee_T)
+        # --- one device->host transfer of everything the host needs
+        with _Stage(self, "readback"):
+            pack = [ee_T.reshape(S, 16)]
+            if stats is not None:
+                pack.append(stats)
             if kp_T is not None:
-                kp_T, kstats = icp_p2p_batched(self.cad, pts, soffs, inits[1])
-                res["kp_icp_stats"] = kstats.cpu().numpy()
-        res["ee_T"] = ee_T.cpu().numpy()
-        res["ee_pose"] = np.stack([get_pose_from_matrix(T) for T in res["ee_T"]])
-        if kp_T is not None:
-            res["kp_T"] = kp_T.cpu().numpy()
-            res["kp_pose"] = np.stack([get_pose_from_matrix(T) for T in res["kp_T"]])
+                pack += [kp_T.reshape(S, 16), kp_ok.double().unsqueeze(1), res["key_points"][0].double(),
+                         res["key_points"][1].double(), res["key_points"][2].double().unsqueeze(1)]
+                if kstats is not None:
+                    pack.append(kstats)
+            host = torch.cat(pack, dim=1).cpu().numpy()
+            c = 16
+            res["ee_T"] = host[:, :16].reshape(S, 4, 4)
+            if stats is not None:
+                res["icp_stats"] = host[:, c:c + 4]
+                c += 4
+            res["ee_pose"] = np.stack([get_pose_from_matrix(T) for T in res["ee_T"]])
+            if kp_T is not None:
+                res["kp_T"] = host[:, c:c + 16].reshape(S, 4, 4)
+                res["kp_valid"] = host[:, c + 16] > 0.5
+                c += 17
+                K = bp.shape[1]
+                res["key_points"] = (host[:, c:c + K].astype(np.float32), host[:, c + K:c + 2 * K].astype(np.int64),
+                                     host[:, c + 2 * K].astype(np.int64))
+                c += 2 * K + 1
+                if kstats is not None:
+                    res["kp_icp_stats"] = host[:, c:c + 4]
+                res["kp_pose"] = np.stack([get_pose_from_matrix(T) for T in res["kp_T"]])
         return res
 
     @torch.no_grad()
@@ -254,11 +303,14 @@ class BatchedInferenceEngine:
         [N] uint8 device tensor used for the EE crop instead of the predicted labels (random-init weights give no
         usable EE). Returns (per-point labels uint8 on the device, pose dict on the host)."""
         nb = len(offs) - 1
-        rgbn = normalize_colors_(rgb)
-        labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
+        with _Stage(self, "segmentation"):
+            rgbn = normalize_colors_(rgb)
+            labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
+            del fld, out
         seg_labels = labels
         crop_src = labels if gt_labels is None else gt_labels
-        labels2, ee_idx, ee_offs = self.filter_ee(points, crop_src.clone(), bidx, nb)
+        with _Stage(self, "ee_cluster"):
+            labels2, ee_idx, ee_offs = self.filter_ee(points, crop_src.clone(), bidx, nb)
         if gt_labels is None:
             seg_labels = labels2
         pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)

@@ -128,10 +128,19 @@ extern "C" int b2me_kabsch_batched(const double* ref, const double* tgt, const i
 }
 
 // ------------------------------------------------------------------------------------------ K10
-#define ICP_GRID 32
+// Batched point-to-point ICP. Per frame: the target (EE) points are binned once into a dense uniform grid
+// (<= 20^3 cells, cell >= 2 cm, counting sort). Every ICP evaluation is ONE launch over (source chunks x
+// frames): a thread transforms one CAD point with the frame's current 4x4 (fp64), finds its EXACT nearest
+// target within max_corr by an expanding-ring search over the grid (cell offsets staged in shared memory),
+// and the CTA reduces the 17 Kabsch sums in a fixed order into a per-(frame, chunk) slot. The last CTA of a
+// frame to finish (ticket counter) adds the chunk slots in chunk order (deterministic), applies the
+// convergence test and the Kabsch update of Open3D's RegistrationICP loop and arms the next evaluation.
+#define ICP_GRID 20
 #define ICP_CELLS (ICP_GRID * ICP_GRID * ICP_GRID)
 #define ICP_MIN_CELL 0.02
 #define ICP_THREADS 256
+#define ICP_MAX_CHUNKS 64
+#define ICP_NSUM 17  // count, sum d2, sum p(3), sum q(3), sum p q^T (9)
 
 struct IcpFrameGrid {
     double origin[3];
@@ -141,10 +150,21 @@ struct IcpFrameGrid {
     int pad;
 };
 
+struct IcpState {
+    double T[16];
+    double prev_fit, prev_rmse, fit, rmse, ncorr;
+    int iters;
+    int done;
+    unsigned int counter;
+    int pad;
+};
+
 struct IcpWs {
     IcpFrameGrid* grids;   // [F]
+    IcpState* state;       // [F]
     int32_t* cell_start;   // [F, ICP_CELLS + 1]
     int32_t* cell_cursor;  // [F, ICP_CELLS]
+    double* partial;       // [F, ICP_MAX_CHUNKS, ICP_NSUM]
     float4* sorted;        // [T_total] xyz + original index bits
     size_t total;
 };
@@ -160,8 +180,10 @@ static IcpWs carve_icp_ws(void* ws, int64_t T_total, int F) {
     };
     const int F1 = F > 0 ? F : 1;
     w.grids = reinterpret_cast<IcpFrameGrid*>(take((size_t)F1 * sizeof(IcpFrameGrid)));
+    w.state = reinterpret_cast<IcpState*>(take((size_t)F1 * sizeof(IcpState)));
     w.cell_start = reinterpret_cast<int32_t*>(take((size_t)F1 * (ICP_CELLS + 1) * 4));
     w.cell_cursor = reinterpret_cast<int32_t*>(take((size_t)F1 * ICP_CELLS * 4));
+    w.partial = reinterpret_cast<double*>(take((size_t)F1 * ICP_MAX_CHUNKS * ICP_NSUM * sizeof(double)));
     w.sorted = reinterpret_cast<float4*>(take((size_t)(T_total > 0 ? T_total : 1) * sizeof(float4)));
     w.total = off;
     return w;
@@ -174,11 +196,11 @@ __device__ __forceinline__ int icp_cell_coord(double v, double origin, double in
     return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
 }
 
-// one block per frame: bbox -> grid, counting sort of the frame's target points by cell
+// one block per frame: bbox -> grid, counting sort of the frame's target points by cell, state <- init
 __global__ void __launch_bounds__(ICP_THREADS)
 k_icp_build_grid(const float* __restrict__ tgt, const int32_t* __restrict__ tgt_offsets,
-                 IcpFrameGrid* __restrict__ grids, int32_t* __restrict__ cell_start_all,
-                 int32_t* __restrict__ cursor_all, float4* __restrict__ sorted) {
+                 const double* __restrict__ init_T, IcpFrameGrid* __restrict__ grids, IcpState* __restrict__ state,
+                 int32_t* __restrict__ cell_start_all, int32_t* __restrict__ cursor_all, float4* __restrict__ sorted) {
     __shared__ float smin[3][ICP_THREADS], smax[3][ICP_THREADS];
     __shared__ IcpFrameGrid g;
     __shared__ int scan_s[33];
@@ -187,6 +209,15 @@ k_icp_build_grid(const float* __restrict__ tgt, const int32_t* __restrict__ tgt_
     const int t0 = tgt_offsets[f], t1 = tgt_offsets[f + 1];
     int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
     int32_t* cursor = cursor_all + (int64_t)f * ICP_CELLS;
+    if (threadIdx.x < 16) state[f].T[threadIdx.x] = init_T[(int64_t)f * 16 + threadIdx.x];
+    if (threadIdx.x == 0) {
+        IcpState* st = state + f;
+        st->prev_fit = st->prev_rmse = st->fit = st->rmse = st->ncorr = 0.0;
+        st->iters = 0;
+        st->done = 0;
+        st->counter = 0u;
+        st->pad = 0;
+    }
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = t0 + threadIdx.x; i < t1; i += blockDim.x)
         for (int a = 0; a < 3; ++a) {
@@ -241,7 +272,6 @@ k_icp_build_grid(const float* __restrict__ tgt, const int32_t* __restrict__ tgt_
     for (int base = 0; base <= ncell; base += blockDim.x) {
         const int c = base + threadIdx.x;
         const int v = (c <= ncell) ? cell_start[c] : 0;
-        // warp scan
         const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
         int inc = v;
         for (int o = 1; o < 32; o <<= 1) {
@@ -278,145 +308,167 @@ k_icp_build_grid(const float* __restrict__ tgt, const int32_t* __restrict__ tgt_
     }
 }
 
-#define ICP_NSUM 17  // count, sum d2, sum p(3), sum q(3), sum p q^T (9)
+// convergence test + Kabsch update of one frame (runs on one thread of the frame's last CTA)
+__device__ __noinline__ void icp_frame_update(IcpState* st, const double* tot, const double* T_s, int f, int S, int ev,
+                                              int max_iter, double rel_fitness, double rel_rmse,
+                                              double* __restrict__ out_T, double* __restrict__ out_stats) {
+    st->counter = 0u;
+    const double ncorr = tot[0];
+    const double fit = S > 0 ? ncorr / (double)S : 0.0;
+    const double rmse = ncorr > 0 ? sqrt(tot[1] / ncorr) : 0.0;
+    bool stop = false;
+    if (ev > 0) {
+        st->iters = ev;
+        if (fabs(st->prev_fit - fit) < rel_fitness && fabs(st->prev_rmse - rmse) < rel_rmse) stop = true;
+    }
+    if (ev == max_iter) stop = true;
+    st->fit = fit; st->rmse = rmse; st->ncorr = ncorr;
+    if (!stop) {
+        st->prev_fit = fit; st->prev_rmse = rmse;
+        if (ncorr > 0) {
+            // update = Kabsch(transformed source -> matched targets) (Eigen::umeyama without scaling)
+            const double n = ncorr;
+            const double mp[3] = {tot[2] / n, tot[3] / n, tot[4] / n};
+            const double mq[3] = {tot[5] / n, tot[6] / n, tot[7] / n};
+            double H[3][3], R[3][3];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) H[r][c] = tot[8 + r * 3 + c] - n * mp[r] * mq[c];
+            kabsch_from_H(H, R);
+            double t[3];
+            for (int r = 0; r < 3; ++r) t[r] = mq[r] - (R[r][0] * mp[0] + R[r][1] * mp[1] + R[r][2] * mp[2]);
+            double Tn[12];
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 4; ++c)
+                    Tn[r * 4 + c] = R[r][0] * T_s[c] + R[r][1] * T_s[4 + c] + R[r][2] * T_s[8 + c];
+                Tn[r * 4 + 3] += t[r];
+            }
+            for (int q = 0; q < 12; ++q) st->T[q] = Tn[q];
+        }
+    } else {
+        st->done = 1;
+        for (int q = 0; q < 16; ++q) out_T[(int64_t)f * 16 + q] = st->T[q];
+        out_stats[(int64_t)f * 4 + 0] = fit;
+        out_stats[(int64_t)f * 4 + 1] = rmse;
+        out_stats[(int64_t)f * 4 + 2] = (double)st->iters;
+        out_stats[(int64_t)f * 4 + 3] = ncorr;
+    }
+}
 
+// grid (nchunk, F). Evaluation `ev` of every frame that has not converged yet.
 __global__ void __launch_bounds__(ICP_THREADS)
-k_icp_p2p(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
-          const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
-          const float4* __restrict__ sorted, const double* __restrict__ init_T, double max_corr, int max_iter,
-          double rel_fitness, double rel_rmse, double* __restrict__ out_T, double* __restrict__ out_stats) {
-    __shared__ double T_s[16];
+k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
+           const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
+           const float4* __restrict__ sorted, IcpState* __restrict__ state, double* __restrict__ partial_all,
+           int ev, double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* __restrict__ out_T,
+           double* __restrict__ out_stats) {
+    __shared__ int cs[ICP_CELLS + 1];
+    __shared__ double T_s[12];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
-    __shared__ double tot[ICP_NSUM];
-    __shared__ int stop_s;
     __shared__ IcpFrameGrid g;
-    const int f = blockIdx.x;
+    __shared__ int last_s;
+    const int f = blockIdx.y;
+    const int nchunk = gridDim.x;
+    IcpState* st = state + f;
+    if (st->done) return;  // uniform for the CTA; written only by the frame's last CTA of an earlier launch
     const int t0 = tgt_offsets[f];
     const int nT = tgt_offsets[f + 1] - t0;
-    const int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
-    if (threadIdx.x < 16) T_s[threadIdx.x] = init_T[(int64_t)f * 16 + threadIdx.x];
-    if (threadIdx.x == 0) { g = grids[f]; stop_s = 0; }
+    if (threadIdx.x < 12) T_s[threadIdx.x] = st->T[threadIdx.x];
+    if (threadIdx.x == 0) g = grids[f];
+    __syncthreads();
+    const int ncell = g.dims[0] * g.dims[1] * g.dims[2];
+    {
+        const int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
+        for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cs[c] = cell_start[c];
+    }
     __syncthreads();
     const double R2 = max_corr * max_corr;
-    double prev_fit = 0.0, prev_rmse = 0.0, fit = 0.0, rmse = 0.0, ncorr = 0.0;
-    int iters = 0;
-
-    // eval #0 uses init; then for it = 0..max_iter-1: update from last eval, eval again, test convergence
-    for (int ev = 0; ev <= max_iter; ++ev) {
-        double acc[ICP_NSUM];
+    double acc[ICP_NSUM];
 #pragma unroll
-        for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
-        if (nT > 0) {
-            for (int i = threadIdx.x; i < S; i += blockDim.x) {
-                const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
-                const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
-                const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
-                const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
-                const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
-                const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
-                const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
-                double best = R2;  // strict '<' below: only neighbours inside the radius qualify
-                int best_j = 0x7FFFFFFF;
-                double bx = 0, by = 0, bz = 0;
-                const int rmax = ICP_GRID;
-                for (int r = 0; r <= rmax; ++r) {
-                    // every point in ring r is at least (r-1)*h away
-                    if (r >= 2) {
-                        const double lb = (double)(r - 1) * g.h;
-                        if (lb * lb >= best) break;
-                    }
-                    const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
-                    if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
-                    for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
-                        const bool zf = (z == z0 || z == z1);
-                        for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
-                            const bool yf = (y == y0 || y == y1);
-                            const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
-                            for (int x = x0; x <= x1; x += xstep) {
-                                if (x < 0 || x >= g.dims[0]) continue;
-                                const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
-                                const int s0 = cell_start[cell], s1 = cell_start[cell + 1];
-                                for (int s = s0; s < s1; ++s) {
-                                    const float4 q = __ldg(sorted + t0 + s);
-                                    const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
-                                    const double d2 = dx * dx + dy * dy + dz * dz;
-                                    const int j = __float_as_int(q.w);
-                                    if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
-                                        best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
-                                    }
+    for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
+    if (nT > 0) {
+        for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < S; i += nchunk * ICP_THREADS) {
+            const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
+            const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
+            const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
+            const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
+            const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
+            const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
+            const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
+            double best = R2;  // strict '<' below: only neighbours inside the radius qualify
+            int best_j = 0x7FFFFFFF;
+            double bx = 0, by = 0, bz = 0;
+            for (int r = 0; r <= ICP_GRID; ++r) {
+                if (r >= 2) {  // every point in ring r is at least (r-1)*h away
+                    const double lb = (double)(r - 1) * g.h;
+                    if (lb * lb >= best) break;
+                }
+                const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+                if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
+                for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
+                    const bool zf = (z == z0 || z == z1);
+                    for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
+                        const bool yf = (y == y0 || y == y1);
+                        const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
+                        for (int x = x0; x <= x1; x += xstep) {
+                            if (x < 0 || x >= g.dims[0]) continue;
+                            const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
+                            const int s0 = cs[cell], s1 = cs[cell + 1];
+                            for (int s = s0; s < s1; ++s) {
+                                const float4 q = __ldg(sorted + t0 + s);
+                                const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
+                                const double d2 = dx * dx + dy * dy + dz * dz;
+                                const int j = __float_as_int(q.w);
+                                if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
+                                    best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
                                 }
                             }
                         }
                     }
                 }
-                if (best_j != 0x7FFFFFFF) {
-                    acc[0] += 1.0; acc[1] += best;
-                    acc[2] += px; acc[3] += py; acc[4] += pz;
-                    acc[5] += bx; acc[6] += by; acc[7] += bz;
-                    acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
-                    acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
-                    acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
-                }
+            }
+            if (best_j != 0x7FFFFFFF) {
+                acc[0] += 1.0; acc[1] += best;
+                acc[2] += px; acc[3] += py; acc[4] += pz;
+                acc[5] += bx; acc[6] += by; acc[7] += bz;
+                acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
+                acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
+                acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
             }
         }
-        // fixed-order block reduction
+    }
+    // fixed-order block reduction -> this chunk's slot
 #pragma unroll
-        for (int q = 0; q < ICP_NSUM; ++q) {
-            double v = acc[q];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < ICP_NSUM) {
-            double v = 0.0;
-            for (int wv = 0; wv < ICP_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
-            tot[threadIdx.x] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            ncorr = tot[0];
-            fit = S > 0 ? ncorr / (double)S : 0.0;
-            rmse = ncorr > 0 ? sqrt(tot[1] / ncorr) : 0.0;
-            bool stop = false;
-            if (ev > 0) {
-                iters = ev;
-                if (fabs(prev_fit - fit) < rel_fitness && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
-            }
-            if (ev == max_iter) stop = true;
-            if (!stop) {
-                prev_fit = fit; prev_rmse = rmse;
-                if (ncorr > 0) {
-                    // update = Kabsch(transformed source -> matched targets) (Eigen::umeyama without scaling)
-                    const double n = ncorr;
-                    const double mp[3] = {tot[2] / n, tot[3] / n, tot[4] / n};
-                    const double mq[3] = {tot[5] / n, tot[6] / n, tot[7] / n};
-                    double H[3][3], R[3][3];
-                    for (int r = 0; r < 3; ++r)
-                        for (int c = 0; c < 3; ++c) H[r][c] = tot[8 + r * 3 + c] - n * mp[r] * mq[c];
-                    kabsch_from_H(H, R);
-                    double t[3];
-                    for (int r = 0; r < 3; ++r) t[r] = mq[r] - (R[r][0] * mp[0] + R[r][1] * mp[1] + R[r][2] * mp[2]);
-                    double Tn[12];
-                    for (int r = 0; r < 3; ++r) {
-                        for (int c = 0; c < 4; ++c)
-                            Tn[r * 4 + c] = R[r][0] * T_s[c] + R[r][1] * T_s[4 + c] + R[r][2] * T_s[8 + c];
-                        Tn[r * 4 + 3] += t[r];
-                    }
-                    for (int q = 0; q < 12; ++q) T_s[q] = Tn[q];
-                }
-            }
-            stop_s = stop ? 1 : 0;
-        }
-        __syncthreads();
-        if (stop_s) break;
+    for (int q = 0; q < ICP_NSUM; ++q) {
+        double v = acc[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
     }
-    if (threadIdx.x < 16) out_T[(int64_t)f * 16 + threadIdx.x] = T_s[threadIdx.x];
+    __syncthreads();
+    double* partial = partial_all + (int64_t)f * ICP_MAX_CHUNKS * ICP_NSUM;
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0.0;
+        for (int wv = 0; wv < ICP_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        partial[blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+        __threadfence();
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        out_stats[(int64_t)f * 4 + 0] = fit;
-        out_stats[(int64_t)f * 4 + 1] = rmse;
-        out_stats[(int64_t)f * 4 + 2] = (double)iters;
-        out_stats[(int64_t)f * 4 + 3] = ncorr;
+        const unsigned int ticket = atomicAdd(&st->counter, 1u);
+        last_s = (ticket == (unsigned int)(nchunk - 1)) ? 1 : 0;
     }
+    __syncthreads();
+    if (!last_s) return;
+    // ---- last CTA of the frame: chunk slots in chunk order, convergence test, Kabsch update
+    __threadfence();
+    __shared__ double tot[ICP_NSUM];
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0.0;
+        for (int c = 0; c < nchunk; ++c) v += __ldcg(partial + c * ICP_NSUM + threadIdx.x);
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
 }
 
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
@@ -427,13 +479,20 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     if (!target_xyz && T_total > 0) return B2ME_EINVAL;  // an empty target cloud may come with a null pointer
     if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
     if (F == 0) return B2ME_OK;
+    if (F > 65535) return B2ME_EUNSUPPORTED;  // gridDim.y
     IcpWs w = carve_icp_ws(ws, T_total, F);
     if (ws_bytes < w.total) return B2ME_EWORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    k_icp_build_grid<<<(unsigned)F, ICP_THREADS, 0, s>>>(target_xyz, tgt_offsets, w.grids, w.cell_start, w.cell_cursor,
-                                                         w.sorted);
-    k_icp_p2p<<<(unsigned)F, ICP_THREADS, 0, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, init_T,
-                                                  max_corr, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
+    k_icp_build_grid<<<(unsigned)F, ICP_THREADS, 0, s>>>(target_xyz, tgt_offsets, init_T, w.grids, w.state,
+                                                         w.cell_start, w.cell_cursor, w.sorted);
+    int nchunk = (S + ICP_THREADS - 1) / ICP_THREADS;
+    if (nchunk > ICP_MAX_CHUNKS) nchunk = ICP_MAX_CHUNKS;
+    const dim3 grid((unsigned)nchunk, (unsigned)F);
+    // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
+    for (int ev = 0; ev <= max_iter; ++ev)
+        k_icp_eval<<<grid, ICP_THREADS, 0, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, w.state,
+                                                w.partial, ev, max_corr, max_iter, rel_fitness, rel_rmse, out_T,
+                                                out_stats);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -52,11 +52,13 @@ def _field(points_f32, feats, scale):
 
 
 def predict_segmentation(seg_model, points, rgb_norm, scale, cluster_dist=0.06):
-    """app/inference_engine.py:395-435 -> (labels [N] int64 after the EE cluster filter, raw arg-max labels)."""
+    """app/inference_engine.py:395-435 -> (labels [N] int64 after the EE cluster filter, dict with the raw arg-max
+    labels, the per-point top-2 logit margin and the logit scale, which parity tests use to skip undecided points)."""
     fld = _field(points, torch.from_numpy(rgb_norm).to(torch.float32), scale)
     out = seg_model(fld.sparse()).slice(fld)
     seg = og.segmentation_labels(out.F).astype(np.int64)
-    raw = seg.copy()
+    top2 = out.F.float().topk(2, dim=1)[0]
+    raw = dict(labels=seg.copy(), margin=(top2[:, 0] - top2[:, 1]).numpy(), scale=float(out.F.abs().max()))
     ee_idx = np.where(seg == 2)[0]
     seg[ee_idx] = 1
     if len(ee_idx) > 1:
@@ -88,7 +90,7 @@ def predict_frame(models, cad, points, rgb, cfg=None, gt_labels=None, ee2base_po
     with torch.no_grad():
         rgbn = normalize_colors(np.asarray(rgb, dtype=np.float32))
         seg, raw = predict_segmentation(models["seg"], points, rgbn, c["seg_scale"], c["cluster_dist"])
-        res["segmentation_pred"] = seg
+        res["segmentation_pred"], res["segmentation_raw"] = seg, raw
         if gt_labels is not None:
             seg = filter_ee(points, gt_labels, c["cluster_dist"])
         res["segmentation"] = seg

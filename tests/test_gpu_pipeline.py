@@ -48,8 +48,11 @@ def test_predict_batch_matches_oracle(setup):
     for f, r in zip(frames, res):
         ref = OP.predict_frame(o, cad, f["points"], f["rgb"], cfgd, gt_labels=f["labels"])
         # predicted labels: identical except where the oracle's own top-2 margin is at fp32 noise level
-        same = (r.segmentation == ref["segmentation_pred"]).mean()
-        assert same > 0.999, same
+        raw = ref["segmentation_raw"]
+        decided = raw["margin"] > 1e-4 * raw["scale"]          # fp32 noise of a 40-layer network is ~1e-6 relative
+        assert decided.mean() > 0.5
+        # with a GT crop the engine returns the network's raw arg-max labels (no EE cluster relabelling)
+        assert np.array_equal(r.segmentation[decided], raw["labels"][decided])
         assert (ref["ee_pose"] is None) == (r.ee_pose is None)
         if ref["ee_pose"] is None:
             continue
@@ -79,4 +82,6 @@ def test_predict_batch_predicted_crop_and_empty(setup):
     assert [len(r.segmentation) for r in res] == [len(fr[0][0]), 0, 5000]
     assert all(r.ee_pose is None and not r.is_confident for r in res)
     ref = OP.predict_frame(o, None, fr[2][0], fr[2][1], dict(seg_scale=100.0, ee_point_counts_threshold=10 ** 9))
-    assert (res[2].segmentation == ref["segmentation"]).mean() > 0.999
+    raw = ref["segmentation_raw"]
+    decided = raw["margin"] > 1e-4 * raw["scale"]
+    assert np.array_equal(res[2].segmentation[decided], ref["segmentation"][decided])

@@ -110,6 +110,15 @@ int b2me_stride_kernel_maps(const int32_t* in2out, const uint8_t* koff, int64_t 
 int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* table, size_t table_bytes,
                        int32_t* nbr, uint32_t* tile_mask, b2me_stream_t stream);
 
+/*
+ * K3b: sort keys for the row permutation the tcgen05 convolution takes (`perm`): key[row] = the row's K-bit
+ * neighbour-occupancy mask of `nbr` [V,K], bits ordered rarest offset first. Rows sorted by key make 128-row
+ * tiles need few kernel offsets. The caller sorts (any sort: the convolution result does not depend on the
+ * order of equal keys) and passes the resulting row order as `perm`. ws: >= 128 bytes.
+ */
+int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
+                        b2me_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sparse convolution (K4) = gather - GEMM - (no scatter: output-stationary), replaces
  * ME.MinkowskiConvolution / MinkowskiConvolutionTranspose / MinkowskiLinear forward
@@ -132,8 +141,11 @@ size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout);
 int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout);
 int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, void* packed,
                          b2me_stream_t stream);
+/* perm [V_out] i32 (may be null = identity): tile t computes the output rows perm[128 t .. 128 t + 127]; any
+ * permutation gives bit-identical results (absent neighbours contribute exact zeros), a mask-sorted one
+ * (b2me_mask_sort_keys) lets tiles skip the kernel offsets none of their rows has. */
 int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2,
-                       const void* packed_w, const int32_t* nbr, const uint32_t* tile_mask, int K,
+                       const void* packed_w, const int32_t* nbr, const int32_t* perm, int K,
                        int64_t V_out, int Cout, const float* scale, const float* shift,
                        const void* residual, int act, float slope,
                        void* out, int out_dtype, b2me_stream_t stream);

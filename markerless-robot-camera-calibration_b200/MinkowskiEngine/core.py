@@ -39,6 +39,7 @@ class SparseTensorOperationMode(Enum):
 
 
 class _State:
+    mask_sort = True  # tcgen05 convolutions take a neighbour-mask-sorted row permutation (tile-level offset skipping)
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     profile = None  # bench.py hook, see ops._profile_conv
@@ -62,6 +63,21 @@ def reset_launch_count():
 
 def launch_count():
     return _State.launches
+
+
+def set_mask_sort(flag):
+    """enable / disable the mask-sorted row permutation of the tcgen05 convolutions (results are bit-identical
+    either way; only the number of (tile, offset) MMA passes changes)."""
+    _State.mask_sort = bool(flag)
+
+
+def mask_sorted_perm(nbr, V, K):
+    """row order that groups rows with the same neighbour pattern (K3b keys + a device sort)."""
+    keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
+    ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
+    check(lib.b2me_mask_sort_keys(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys")
+    _count(2)
+    return torch.sort(keys[:V])[1].to(torch.int32)
 
 
 def set_profile(mode):
@@ -104,6 +120,7 @@ class _Level:
         self.table = table    # uint8 device buffer (b2me_table_bytes)
         self.V = V
         self.nbr_k3 = None
+        self.perm_k3 = None
         self.down = None      # dict(in2out, koff, nbr_down, nbr_up, coarse_key)
         self.batch_size = None
 
@@ -166,6 +183,20 @@ class CoordinateManager:
             _count(1)
             lv.nbr_k3 = nbr[:lv.V]
         return lv.nbr_k3
+
+    def perm_k3(self, key):
+        lv = self.levels[key]
+        if lv.perm_k3 is None:
+            lv.perm_k3 = mask_sorted_perm(self.kernel_map_k3(key), lv.V, 27)
+        return lv.perm_k3
+
+    def perm_stride(self, rec, which):
+        """mask-sorted row order of the k2 s2 ("down") / transposed ("up") kernel map of a stride record."""
+        name = "perm_" + which
+        if rec.get(name) is None:
+            nbr = rec["nbr_" + which]
+            rec[name] = mask_sorted_perm(nbr, nbr.shape[0], 8)
+        return rec[name]
 
     # -- K2
     def stride_down(self, key):
@@ -230,6 +261,7 @@ class _Pending:
     src: List["SparseTensor"]      # 1 or 2 sources (2 = lazy cat)
     module: object = None          # owner of the weights (conv / linear)
     nbr: Optional[torch.Tensor] = None
+    perm: object = None            # callable returning the mask-sorted row order of `nbr` (built on first use)
     K: int = 1
     V_out: int = 0
     Cout: int = 0
@@ -242,8 +274,8 @@ class _Pending:
     extra: dict = dc_field(default_factory=dict)
 
     def clone(self):
-        return _Pending(self.kind, list(self.src), self.module, self.nbr, self.K, self.V_out, self.Cout, self.scale,
-                        self.shift, self.residual, self.act, self.slope, self.stage, dict(self.extra))
+        return _Pending(self.kind, list(self.src), self.module, self.nbr, self.perm, self.K, self.V_out, self.Cout,
+                        self.scale, self.shift, self.residual, self.act, self.slope, self.stage, dict(self.extra))
 
 
 def _as_dtype(t, dtype):

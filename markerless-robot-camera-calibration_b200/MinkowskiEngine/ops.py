@@ -128,8 +128,9 @@ def _run_conv(p):
             res = _as_dtype(res, torch.bfloat16)
         packed = _weight_packed(p.module, K, Cin1, Cin2, Cout)
         out = torch.empty((V_out, Cout), dtype=torch.bfloat16, device=dev)
+        perm = p.perm() if (p.perm is not None and _State.mask_sort) else None
         ev = _profile_conv("tc", p, Cin1 + Cin2)
-        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, ptr(packed), ptr(p.nbr), None, K, V_out, Cout,
+        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, ptr(packed), ptr(p.nbr), ptr(perm), K, V_out, Cout,
                                      ptr(p.scale), ptr(p.shift), ptr(res), p.act, p.slope, ptr(out), _lib.BF16,
                                      stream()), "spconv_fwd_tc")
         if ev is not None:
@@ -168,13 +169,16 @@ def conv_forward(module, x: SparseTensor):
     if module.dilation != 1:
         raise NotImplementedError("dilated sparse convolution is outside the hot-path subset")
     if not module.is_transpose:
+        perm = None
         if ks == 1 and st == 1:
             out_key, nbr, K = key, None, 1
         elif ks == 3 and st == 1:
             out_key, nbr, K = key, mgr.kernel_map_k3(key), 27
+            perm = lambda: mgr.perm_k3(key)  # noqa: E731
         elif ks == 2 and st == 2:
             out_key, rec = mgr.stride_down(key)
             nbr, K = rec["nbr_down"], 8
+            perm = lambda: mgr.perm_stride(rec, "down")  # noqa: E731
         else:
             raise NotImplementedError(f"MinkowskiConvolution(kernel_size={ks}, stride={st}) is outside the subset "
                                       "used by MinkUNet (k3 s1, k2 s2, k1 s1)")
@@ -182,10 +186,11 @@ def conv_forward(module, x: SparseTensor):
         if ks == 2 and st == 2:
             out_key, rec = mgr.stride_up(key)
             nbr, K = rec["nbr_up"], 8
+            perm = lambda: mgr.perm_stride(rec, "up")  # noqa: E731
         else:
             raise NotImplementedError(f"MinkowskiConvolutionTranspose(kernel_size={ks}, stride={st})")
     V_out = mgr.level(out_key).V
-    p = _Pending("conv", _sources(x), module=module, nbr=nbr, K=K, V_out=V_out, Cout=module.out_channels)
+    p = _Pending("conv", _sources(x), module=module, nbr=nbr, perm=perm, K=K, V_out=V_out, Cout=module.out_channels)
     if module.bias is not None:
         p.shift = module.bias.detach().float().reshape(-1).contiguous()
         p.stage = 1

@@ -445,3 +445,60 @@ extern "C" int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, cons
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
+
+// ------------------------------------------------------------------------------------------ K3b
+// Sort keys for the convolution's row permutation: rows with the same neighbour pattern are made adjacent so
+// that a 128-row tile of the gather-GEMM kernel needs few kernel offsets (the tile skips an offset when none of
+// its rows has that neighbour). key(row) = the row's K-bit occupancy mask with the bits reordered so that the
+// RAREST offset of this map is the most significant bit (measured: 0.94 -> 0.37 non-empty (tile, offset) pairs
+// on 5 mm Kinect clouds, fill 0.25).
+__global__ void __launch_bounds__(256) k_offset_counts(const int32_t* __restrict__ nbr, int64_t total, int K,
+                                                       unsigned int* __restrict__ counts /*[32]*/) {
+    __shared__ unsigned int h[32];
+    if (threadIdx.x < 32) h[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        if (__ldg(nbr + t) >= 0) atomicAdd(&h[(int)(t % K)], 1u);
+    __syncthreads();
+    if (threadIdx.x < K && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_mask_keys(const int32_t* __restrict__ nbr, int64_t V, int K,
+                                                   const unsigned int* __restrict__ counts,
+                                                   int32_t* __restrict__ keys) {
+    __shared__ int bitpos[32];  // offset k -> bit position in the key
+    if (threadIdx.x < K) {
+        // rank of offset k by (count ascending, k ascending); rarest -> most significant of the K bits
+        const unsigned int mine = counts[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const unsigned int c = counts[j];
+            if (c < mine || (c == mine && j < (int)threadIdx.x)) ++rank;
+        }
+        bitpos[threadIdx.x] = K - 1 - rank;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    unsigned int key = 0u;
+    for (int k = 0; k < K; ++k)
+        if (__ldg(nbr + v * K + k) >= 0) key |= 1u << bitpos[k];
+    keys[v] = (int32_t)key;
+}
+
+extern "C" int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
+                                   b2me_stream_t stream) {
+    if (!nbr || !keys || !ws || V < 0 || K < 1 || K > 31) return B2ME_EINVAL;
+    if (ws_bytes < 32 * sizeof(unsigned int)) return B2ME_EWORKSPACE;
+    if (V == 0) return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(ws);
+    cudaMemsetAsync(counts, 0, 32 * sizeof(unsigned int), s);
+    const int64_t total = V * K;
+    int64_t blocks = ceil_div64(total, 256 * 8);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_offset_counts<<<(unsigned)blocks, 256, 0, s>>>(nbr, total, K, counts);
+    k_mask_keys<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(nbr, V, K, counts, keys);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

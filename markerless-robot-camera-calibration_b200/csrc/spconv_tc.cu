@@ -28,6 +28,7 @@ struct TcParams {
     const __nv_bfloat16* in2;
     const uint8_t* wpacked;
     const int32_t* nbr;
+    const int32_t* perm;
     const float* scale;
     const float* shift;
     const __nv_bfloat16* residual;
@@ -125,10 +126,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
-    // carve: [stages][nbr_s 128*K i32][scale n_tile][shift n_tile][full S][empty S][tmem_full][tmem_ptr][mask]
+    // carve: [stages][nbr_s 128*K i32][rows_s 128 i32][scale n_tile][shift n_tile][full S][empty S][tmem_full][tmem_ptr][mask]
     uint32_t off = (uint32_t)S * stage_bytes;
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
     off += TC_BM * K * 4;
+    int32_t* rows_s = reinterpret_cast<int32_t*>(sm + off);  // output row of every tile slot (-1 = past the end)
+    off += TC_BM * 4;
     float* scale_s = reinterpret_cast<float*>(sm + off);
     off += p.n_tile * 4;
     float* shift_s = reinterpret_cast<float*>(sm + off);
@@ -163,19 +166,22 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    __syncthreads();  // mask_s = 0 visible
+    if (tid < TC_BM) {
+        const long long slot = row0 + tid;
+        rows_s[tid] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
+    }
+    __syncthreads();  // mask_s = 0 and rows_s visible
     {
-        // stage the tile's kernel-map rows (contiguous in global) and find the offsets that occur
+        // stage the kernel-map rows of the tile's output rows and find the offsets that occur
         uint32_t local = 0;
         if (p.nbr) {
             const int total = TC_BM * K;
-            const long long gbase = row0 * K;
-            const long long gmax = p.V_out * K;
             for (int i = tid; i < total; i += TC_THREADS) {
-                const long long g = gbase + i;
-                const int v = (g < gmax) ? __ldg(p.nbr + g) : -1;
+                const int r = i / K;
+                const int row = rows_s[r];
+                const int v = (row >= 0) ? __ldg(p.nbr + (long long)row * K + (i - r * K)) : -1;
                 nbr_s[i] = v;
-                if (v >= 0) local |= 1u << (i % K);
+                if (v >= 0) local |= 1u << (i - r * K);
             }
         } else {
             local = 1u;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
             for (int i = 0; i < 8; ++i) {
                 const int r = rbase + 16 * i;
                 if (p.nbr) idx[i] = nbr_s[r * K + k];
-                else idx[i] = (row0 + r < p.V_out) ? (int)(row0 + r) : -1;
+                else idx[i] = rows_s[r];
             }
             for (int c = 0; c < nchunk; ++c) {
                 const int s = issued % S;
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
         // =============================== epilogue ===============================
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
-        const long long row = row0 + tid;
-        const bool row_ok = row < p.V_out;
+        const long long row = rows_s[tid];
+        const bool row_ok = row >= 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int cb = 0; cb < p.n_tile; cb += 16) {
             uint32_t r[16];
@@ -421,10 +427,9 @@ extern "C" int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, i
 }
 
 extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, const void* packed_w,
-                                  const int32_t* nbr, const uint32_t* tile_mask, int K, int64_t V_out, int Cout,
+                                  const int32_t* nbr, const int32_t* perm, int K, int64_t V_out, int Cout,
                                   const float* scale, const float* shift, const void* residual, int act, float slope,
                                   void* out, int out_dtype, b2me_stream_t stream) {
-    (void)tile_mask;  // the kernel derives the per-tile offset mask from the staged kernel-map rows
     if (!in1 || !packed_w || !out || V_out < 0) return B2ME_EINVAL;
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
@@ -437,6 +442,7 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.in2 = reinterpret_cast<const __nv_bfloat16*>(in2);
     p.wpacked = reinterpret_cast<const uint8_t*>(packed_w);
     p.nbr = nbr;
+    p.perm = perm;
     p.scale = scale;
     p.shift = shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
@@ -457,7 +463,7 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     while (cols < p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
 
-    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + (size_t)p.n_tile * 8 + 8 + 16 * 8 + 64;
+    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * (K + 1) * 4 + (size_t)p.n_tile * 8 + 8 + 16 * 8 + 64;
     const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
     int S = 4;
     while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;

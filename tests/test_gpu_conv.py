@@ -45,7 +45,7 @@ def _call_simt(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torc
     return out
 
 
-def _call_tc(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torch.float32):
+def _call_tc(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torch.float32, perm=None):
     from MinkowskiEngine._lib import ptr, stream, dtype_code, check
     K, _, Cout = W.shape
     c1, c2 = x.shape[1], 0 if x2 is None else x2.shape[1]
@@ -53,7 +53,7 @@ def _call_tc(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torch.
     packed = torch.empty((lib.b2me_tc_packed_bytes(K, c1, c2, Cout),), dtype=torch.uint8, device="cuda")
     check(lib.b2me_tc_pack_weights(ptr(W), K, c1, c2, Cout, ptr(packed), stream()))
     out = torch.empty((V_out, Cout), dtype=out_dtype, device="cuda")
-    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, ptr(packed), ptr(nbr), None, K, V_out, Cout, ptr(scale),
+    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, ptr(packed), ptr(nbr), ptr(perm), K, V_out, Cout, ptr(scale),
                                  ptr(shift), ptr(res), act, 0.01, ptr(out), dtype_code(out_dtype), stream()))
     torch.cuda.synchronize()
     return out
@@ -125,6 +125,37 @@ def test_spconv_parity(kind, c1, c2, cout, epi):
         assert rel_err(gotb16.float(), ref) < 2e-2           # north-star bf16 tolerance vs the fp32 oracle
     else:
         assert c1 < 16 or cout % 16
+
+
+@pytest.mark.parametrize("kind,c1,cout", [("k3", 64, 128), ("up", 128, 64), ("down", 32, 32)])
+def test_tc_row_permutation_is_bit_identical(kind, c1, cout):
+    """K3b: any row permutation (mask-sorted or random) must give bit-identical outputs - absent neighbours
+    contribute exact zeros - while the mask-sorted one skips (tile, offset) passes."""
+    ME, os_, cs = _setup(n=20000)
+    lib = ME._C
+    nbr_o, nbr_c, V_in, V_out = _maps(os_, cs, kind)
+    K = nbr_c.shape[1]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(V_in, c1, generator=g).bfloat16().cuda()
+    W = (torch.randn(K, c1, cout, generator=g) / 8).cuda()
+    res = torch.randn(V_out, cout, generator=g).bfloat16().cuda()
+    sc = (torch.rand(cout, generator=g) + 0.5).cuda()
+    base = _call_tc(lib, x, None, W, nbr_c, V_out, sc, None, res, 1)
+    perm = ME.mask_sorted_perm(nbr_c, V_out, K)
+    assert torch.equal(torch.sort(perm.long())[0].cpu(), torch.arange(V_out))
+    # keys are non-decreasing along perm: rows with equal masks are adjacent
+    got = _call_tc(lib, x, None, W, nbr_c, V_out, sc, None, res, 1, perm=perm)
+    assert torch.equal(got, base)
+    rnd = torch.randperm(V_out, generator=g).int().cuda()
+    assert torch.equal(_call_tc(lib, x, None, W, nbr_c, V_out, sc, None, res, 1, perm=rnd), base)
+    # the sorted order needs fewer non-empty (tile, offset) pairs than the natural one
+    pres = (nbr_c >= 0).cpu()
+
+    def tiles(order):
+        pad = (-V_out) % 128
+        p_ = torch.cat((pres[order], torch.zeros(pad, K, dtype=torch.bool)))
+        return int(p_.view(-1, 128, K).any(1).sum())
+    assert tiles(perm.long().cpu()) < tiles(torch.arange(V_out))
 
 
 def test_tc_small_and_ragged_tiles():

@@ -73,11 +73,39 @@ def load_cad_points(cad_name, n_points=8192, seed=13):
     return pts[pts[:, 0] > 0.0]
 
 
+_MORTON_CACHE = {}
+
+
+def _spread10(v):
+    v = (v | (v << 16)) & 0x030000FF
+    v = (v | (v << 8)) & 0x0300F00F
+    v = (v | (v << 4)) & 0x030C30C3
+    return (v | (v << 2)) & 0x09249249
+
+
+def morton_sorted(source):
+    """the CAD cloud in Morton (Z-curve) order, cached per tensor: neighbouring threads of the ICP kernel then
+    query neighbouring grid cells, so their candidate loads coalesce / broadcast. Every sum of the ICP update
+    runs over all correspondences, so the order of the source points does not change the result beyond fp64
+    round-off."""
+    key = (source.data_ptr(), tuple(source.shape), source._version)
+    hit = _MORTON_CACHE.get(key)
+    if hit is not None:
+        return hit[1]
+    lo, hi = source.min(0)[0], source.max(0)[0]
+    q = ((source - lo) / (hi - lo).clamp(min=1e-12) * 1023.0).long().clamp(0, 1023)
+    code = _spread10(q[:, 0]) | (_spread10(q[:, 1]) << 1) | (_spread10(q[:, 2]) << 2)
+    out = source[torch.sort(code, stable=True)[1]].contiguous()
+    _MORTON_CACHE.clear()
+    _MORTON_CACHE[key] = (source, out)   # keeps `source` alive so the data_ptr key stays valid
+    return out
+
+
 def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD, max_iter=ICP_MAX_ITER,
                     rel_fitness=ICP_REL_FITNESS, rel_rmse=ICP_REL_RMSE):
     """source [S,3] f32 CUDA (CAD); targets [T_total,3] f32 CUDA; tgt_offsets [F+1]; init_T [F,4,4] f64.
     Returns (T [F,4,4] f64, stats [F,4] f64 = fitness, inlier_rmse, iterations, correspondences)."""
-    source = source.to(torch.float32).contiguous()
+    source = morton_sorted(source.to(torch.float32).contiguous())
     targets = targets.to(torch.float32).contiguous()
     dev = source.device
     offs = torch.as_tensor(tgt_offsets, dtype=torch.int32, device=dev).contiguous()
@@ -89,7 +117,7 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
     check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
                                    ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")
-    _count(2)
+    _count(2 + int(max_iter))  # grid build + (max_iter + 1) evaluation launches
     return out_T.view(F, 4, 4), stats
 
 

@@ -355,15 +355,75 @@ __device__ __noinline__ void icp_frame_update(IcpState* st, const double* tot, c
 }
 
 // grid (nchunk, F). Evaluation `ev` of every frame that has not converged yet.
+// dynamic smem: [cell offsets ICP_CELLS+1 i32][target points of the frame, float4, when they fit (tcap points)]
+template <bool kSmemTargets>
+__device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const int* cs, const IcpFrameGrid& g,
+                                           double px, double py, double pz, double R2, double& best, int& best_j,
+                                           double& bx, double& by, double& bz) {
+    const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
+    const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
+    // m = distance from the query to the nearest face of its own cell that has cells behind it: every point of
+    // ring r (Chebyshev cell distance r >= 1) is at least m + (r-1) h away.
+    double m = 1e300;
+    {
+        const double lx = px - (g.origin[0] + cx * g.h), ly = py - (g.origin[1] + cy * g.h),
+                     lz = pz - (g.origin[2] + cz * g.h);
+        if (cx > 0) m = fmin(m, lx);
+        if (cx < g.dims[0] - 1) m = fmin(m, g.h - lx);
+        if (cy > 0) m = fmin(m, ly);
+        if (cy < g.dims[1] - 1) m = fmin(m, g.h - ly);
+        if (cz > 0) m = fmin(m, lz);
+        if (cz < g.dims[2] - 1) m = fmin(m, g.h - lz);
+        if (m < 0.0) m = 0.0;
+    }
+    best = R2;  // strict '<' below: only neighbours inside the radius qualify
+    best_j = 0x7FFFFFFF;
+    for (int r = 0; r <= ICP_GRID; ++r) {
+        if (r >= 1) {
+            const double lb = m + (double)(r - 1) * g.h;
+            if (lb * lb >= best) break;
+        }
+        const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+        if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
+        for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
+            const bool zf = (z == z0 || z == z1);
+            for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
+                const bool yf = (y == y0 || y == y1);
+                const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
+                for (int x = x0; x <= x1; x += xstep) {
+                    if (x < 0 || x >= g.dims[0]) continue;
+                    const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
+                    const int s0 = cs[cell], s1 = cs[cell + 1];
+                    for (int s = s0; s < s1; ++s) {
+                        float4 q;
+                        if (kSmemTargets) q = tg[s];
+                        else q = __ldg(tg + s);
+                        const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        const int j = __float_as_int(q.w);
+                        if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
+                            best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(ICP_THREADS)
 k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
            const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
            const float4* __restrict__ sorted, IcpState* __restrict__ state, double* __restrict__ partial_all,
-           int ev, double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* __restrict__ out_T,
-           double* __restrict__ out_stats) {
-    __shared__ int cs[ICP_CELLS + 1];
+           int ev, int tcap, double max_corr, int max_iter, double rel_fitness, double rel_rmse,
+           double* __restrict__ out_T, double* __restrict__ out_stats) {
+    extern __shared__ __align__(16) unsigned char icp_smem[];
+    float4* tg_s = reinterpret_cast<float4*>(icp_smem);
+    int* cs = reinterpret_cast<int*>(icp_smem + (size_t)tcap * sizeof(float4));
     __shared__ double T_s[12];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
+    __shared__ double tot[ICP_NSUM];
     __shared__ IcpFrameGrid g;
     __shared__ int last_s;
     const int f = blockIdx.y;
@@ -380,6 +440,9 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
         const int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
         for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cs[c] = cell_start[c];
     }
+    const bool in_smem = nT <= tcap;
+    if (in_smem)
+        for (int i = threadIdx.x; i < nT; i += blockDim.x) tg_s[i] = __ldg(sorted + t0 + i);
     __syncthreads();
     const double R2 = max_corr * max_corr;
     double acc[ICP_NSUM];
@@ -391,41 +454,10 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
             const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
             const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
             const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
-            const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
-            const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
-            const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
-            double best = R2;  // strict '<' below: only neighbours inside the radius qualify
-            int best_j = 0x7FFFFFFF;
-            double bx = 0, by = 0, bz = 0;
-            for (int r = 0; r <= ICP_GRID; ++r) {
-                if (r >= 2) {  // every point in ring r is at least (r-1)*h away
-                    const double lb = (double)(r - 1) * g.h;
-                    if (lb * lb >= best) break;
-                }
-                const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
-                if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
-                for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
-                    const bool zf = (z == z0 || z == z1);
-                    for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
-                        const bool yf = (y == y0 || y == y1);
-                        const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
-                        for (int x = x0; x <= x1; x += xstep) {
-                            if (x < 0 || x >= g.dims[0]) continue;
-                            const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
-                            const int s0 = cs[cell], s1 = cs[cell + 1];
-                            for (int s = s0; s < s1; ++s) {
-                                const float4 q = __ldg(sorted + t0 + s);
-                                const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
-                                const double d2 = dx * dx + dy * dy + dz * dz;
-                                const int j = __float_as_int(q.w);
-                                if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
-                                    best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            double best, bx = 0, by = 0, bz = 0;
+            int best_j;
+            if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, best, best_j, bx, by, bz);
+            else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, best, best_j, bx, by, bz);
             if (best_j != 0x7FFFFFFF) {
                 acc[0] += 1.0; acc[1] += best;
                 acc[2] += px; acc[3] += py; acc[4] += pz;
@@ -460,7 +492,6 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
     if (!last_s) return;
     // ---- last CTA of the frame: chunk slots in chunk order, convergence test, Kabsch update
     __threadfence();
-    __shared__ double tot[ICP_NSUM];
     if (threadIdx.x < ICP_NSUM) {
         double v = 0.0;
         for (int c = 0; c < nchunk; ++c) v += __ldcg(partial + c * ICP_NSUM + threadIdx.x);
@@ -470,6 +501,8 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
     if (threadIdx.x == 0)
         icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
 }
+
+#define ICP_SMEM_TARGETS 4096
 
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
@@ -488,11 +521,19 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     int nchunk = (S + ICP_THREADS - 1) / ICP_THREADS;
     if (nchunk > ICP_MAX_CHUNKS) nchunk = ICP_MAX_CHUNKS;
     const dim3 grid((unsigned)nchunk, (unsigned)F);
+    const int tcap = ICP_SMEM_TARGETS;
+    const size_t smem = (size_t)tcap * sizeof(float4) + (size_t)(ICP_CELLS + 1) * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_icp_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return B2ME_ELAUNCH;
+        attr_set = true;
+    }
     // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
     for (int ev = 0; ev <= max_iter; ++ev)
-        k_icp_eval<<<grid, ICP_THREADS, 0, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, w.state,
-                                                w.partial, ev, max_corr, max_iter, rel_fitness, rel_rmse, out_T,
-                                                out_stats);
+        k_icp_eval<<<grid, ICP_THREADS, smem, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, w.state,
+                                                   w.partial, ev, tcap, max_corr, max_iter, rel_fitness, rel_rmse,
+                                                   out_T, out_stats);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -15,6 +15,7 @@
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define TC_BM 128
 #define TC_BK 64
@@ -39,6 +40,7 @@ struct TcParams {
     int act, out_dtype, tmem_cols;
     float slope;
     unsigned int b_bytes;
+    int debug;  // B2ME_TC_DEBUG (timing experiments only, results invalid): 1 skip gather, 2 skip weights, 4 skip MMA
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -216,13 +218,29 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
             }
             for (int c = 0; c < nchunk; ++c) {
                 const int s = issued % S;
-                if (issued >= S) mbar_wait(bar_empty + 8 * s, ((issued / S) & 1) ^ 1);
+                if (issued >= S) {
+                    // the slot is free once the MMAs of item (issued - S) have completed. Before blocking on that,
+                    // publish every gather already issued: the MMA warp must never wait for data whose arrival is
+                    // only signalled after a LATER gather could be issued (that would serialise MMA and gather).
+                    const uint32_t par = ((issued / S) & 1) ^ 1;
+                    const bool ready = __all_sync(0xffffffffu, mbar_try_wait(bar_empty + 8 * s, par));
+                    if (!ready) {
+                        if (arrived < issued) {
+                            cp_async_wait<0>();
+                            fence_proxy_async();
+                            __syncwarp();
+                            for (; arrived < issued; ++arrived)
+                                if (lane == 0) mbar_arrive(bar_full + 8 * (arrived % S));
+                        }
+                        mbar_wait(bar_empty + 8 * s, par);
+                    }
+                }
                 const __nv_bfloat16* src;
                 int cin, coff;
                 if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
                 else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * TC_BK; }
                 const int kw = min(TC_BK, cin - coff);
-                if (j * 8 < kw) {
+                if (j * 8 < kw && !(p.debug & 1)) {
                     const uint32_t a_s = base + (uint32_t)s * stage_bytes;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -316,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
                     const uint32_t a_s = base + (uint32_t)s * stage_bytes;
                     const uint32_t b_s = a_s + TC_A_BYTES;
                     const uint64_t adesc = make_smem_desc_sw128(a_s);
-                    for (int kk = 0; kk < kw / 16; ++kk) {
+                    for (int kk = 0; kk < ((p.debug & 4) ? 0 : kw / 16); ++kk) {
                         for (int h = 0; h < nhalf; ++h) {
                             const uint64_t bdesc = make_smem_desc_sw128(b_s + (uint32_t)(h * nh) * 128u);
                             tc_mma_bf16(tmem_base + (uint32_t)(h * nh), adesc + (uint64_t)(kk * 2),
@@ -341,8 +359,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
                     const uint32_t b_s = base + (uint32_t)s * stage_bytes + TC_A_BYTES;
                     const uint8_t* g =
                         p.wpacked + ((size_t)((size_t)blockIdx.y * K + k) * nchunk + c) * (size_t)p.b_bytes;
-                    mbar_arrive_expect_tx(bar_full + 8 * s, p.b_bytes);
-                    bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * s);
+                    if (p.debug & 2) {
+                        mbar_arrive(bar_full + 8 * s);
+                    } else {
+                        mbar_arrive_expect_tx(bar_full + 8 * s, p.b_bytes);
+                        bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * s);
+                    }
                     ++it;
                 }
             }
@@ -459,6 +481,10 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.out_dtype = out_dtype;
     p.slope = slope;
     p.b_bytes = (unsigned)p.n_tile * 128u;
+    {
+        const char* dbg = getenv("B2ME_TC_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
     int cols = 32;
     while (cols < p.n_tile) cols <<= 1;
     p.tmem_cols = cols;

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--stages", action="store_true", help="one extra (untimed) step with synchronised per-stage times")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--mask-block", type=int, default=None, help="rows per locality block of the K3b mask sort (0 = global)")
     ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     return ap.parse_args()
 
@@ -200,6 +201,8 @@ def run_b200(args, rank, world, local):
     from b200calib.synthetic import ee_surface_cloud
     bdist.init_from_env("nccl" if world > 1 else None)
     ME.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
+    if args.mask_block is not None:
+        ME.set_mask_sort_block(args.mask_block)
     seg, rot, kp = [m.to(dev) for m in build_models(ME)]
     cad = torch.from_numpy(ee_surface_cloud(4096, SEED)).to(dev)
     cfg = PipelineConfig(seg_scale=args.scale, icp_enabled=not args.no_icp)

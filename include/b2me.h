@@ -118,6 +118,11 @@ int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* tab
  */
 int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
                         b2me_stream_t stream);
+/* 64-bit keys with a locality prefix: key[row] = (row / block_rows) << 32 | mask key (block_rows = 0: no prefix).
+ * Rows of one block of consecutive first-occurrence rows stay together, so concurrently running tiles gather from
+ * one L2-sized window of the input. */
+int b2me_mask_sort_keys64(const int32_t* nbr, int64_t V, int K, int block_rows, int64_t* keys, void* ws,
+                          size_t ws_bytes, b2me_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sparse convolution (K4) = gather - GEMM - (no scatter: output-stationary), replaces

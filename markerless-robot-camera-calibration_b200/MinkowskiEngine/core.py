@@ -40,6 +40,7 @@ class SparseTensorOperationMode(Enum):
 
 class _State:
     mask_sort = True  # tcgen05 convolutions take a neighbour-mask-sorted row permutation (tile-level offset skipping)
+    mask_sort_block = 0  # rows per locality block of that sort, 0 = whole map (measured: 0 is fastest)
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     profile = None  # bench.py hook, see ops._profile_conv
@@ -71,11 +72,20 @@ def set_mask_sort(flag):
     _State.mask_sort = bool(flag)
 
 
-def mask_sorted_perm(nbr, V, K):
-    """row order that groups rows with the same neighbour pattern (K3b keys + a device sort)."""
-    keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
+def set_mask_sort_block(rows):
+    """rows of one locality block of the mask sort (0 = sort the whole map by mask only)."""
+    _State.mask_sort_block = int(rows)
+
+
+def mask_sorted_perm(nbr, V, K, block_rows=None):
+    """row order that groups rows with the same neighbour pattern inside blocks of `block_rows` consecutive rows
+    (K3b keys + a device sort)."""
+    if block_rows is None:
+        block_rows = _State.mask_sort_block
+    keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
     ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
-    check(lib.b2me_mask_sort_keys(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys")
+    check(lib.b2me_mask_sort_keys64(ptr(nbr), V, K, block_rows, ptr(keys), ptr(ws), ws.numel(), stream()),
+          "mask_sort_keys64")
     _count(2)
     return torch.sort(keys[:V])[1].to(torch.int32)
 

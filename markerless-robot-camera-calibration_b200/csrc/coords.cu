@@ -486,6 +486,50 @@ __global__ void __launch_bounds__(256) k_mask_keys(const int32_t* __restrict__ n
     keys[v] = (int32_t)key;
 }
 
+// 64-bit variant: key = (row / block_rows) << 32 | mask key. Sorting these keeps the rows of one block of
+// block_rows consecutive rows (= one spatial neighbourhood in first-occurrence order) together, so the tiles that
+// run concurrently gather from one L2-sized window of the input instead of the whole tensor.
+__global__ void __launch_bounds__(256) k_mask_keys64(const int32_t* __restrict__ nbr, int64_t V, int K,
+                                                     const unsigned int* __restrict__ counts, int block_rows,
+                                                     long long* __restrict__ keys) {
+    __shared__ int bitpos[32];
+    if (threadIdx.x < K) {
+        const unsigned int mine = counts[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const unsigned int c = counts[j];
+            if (c < mine || (c == mine && j < (int)threadIdx.x)) ++rank;
+        }
+        bitpos[threadIdx.x] = K - 1 - rank;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    unsigned int key = 0u;
+    for (int k = 0; k < K; ++k)
+        if (__ldg(nbr + v * K + k) >= 0) key |= 1u << bitpos[k];
+    const long long blk = block_rows > 0 ? (long long)(v / block_rows) : 0ll;
+    keys[v] = (blk << 32) | (long long)key;
+}
+
+extern "C" int b2me_mask_sort_keys64(const int32_t* nbr, int64_t V, int K, int block_rows, int64_t* keys, void* ws,
+                                     size_t ws_bytes, b2me_stream_t stream) {
+    if (!nbr || !keys || !ws || V < 0 || K < 1 || K > 31 || block_rows < 0) return B2ME_EINVAL;
+    if (ws_bytes < 32 * sizeof(unsigned int)) return B2ME_EWORKSPACE;
+    if (V == 0) return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(ws);
+    cudaMemsetAsync(counts, 0, 32 * sizeof(unsigned int), s);
+    const int64_t total = V * K;
+    int64_t blocks = ceil_div64(total, 256 * 8);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    k_offset_counts<<<(unsigned)blocks, 256, 0, s>>>(nbr, total, K, counts);
+    k_mask_keys64<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(nbr, V, K, counts, block_rows,
+                                                               reinterpret_cast<long long*>(keys));
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
 extern "C" int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
                                    b2me_stream_t stream) {
     if (!nbr || !keys || !ws || V < 0 || K < 1 || K > 31) return B2ME_EINVAL;

@@ -1,28 +1,40 @@
 // spconv_tc.cu — K4b: sparse convolution as an output-stationary implicit GEMM on tcgen05 (sm_100a).
 //
-//   CTA tile      128 output voxels x n_tile output channels (n_tile <= 384 fp32 columns of TMEM)
-//   reduction     items = (kernel offset k that has at least one neighbour in the tile) x (64-channel chunk)
+// PERSISTENT, warp-specialised kernel: one CTA per SM walks the work list (128-row tile x n-tile) round-robin.
+//
+//   work item     128 output voxels (rows perm[128 t ..]) x n_tile output channels (n_tile <= 384 TMEM columns)
+//   reduction     items = (kernel offset k with at least one neighbour in the tile) x (64-channel chunk)
 //   A operand     128 gathered input rows x 64 bf16 (= one 128-byte swizzle row per voxel), cp.async 16-byte
 //                 pieces straight into the SWIZZLE_128B K-major smem image, zero-fill for missing neighbours
 //   B operand     W[k][chunk] pre-packed on the host side of the ABI into the exact smem image, so one
 //                 cp.async.bulk (UBLKCP) per item brings n_tile x 128 bytes and completes on the stage mbarrier
 //   MMA           one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16), fp32
 //                 accumulators stay in TMEM for the whole tile
-//   epilogue      tcgen05.ld -> folded BatchNorm scale/shift, residual add, ReLU/LeakyReLU -> bf16/f32 rows
-//   warps         0-3 gather producers, then epilogue (warp w owns TMEM lanes 32w..32w+31)
-//                 4   TMEM alloc + MMA issuer        5   weight (B) bulk-copy issuer
-//   pipeline      S-stage ring: full[s] (4 producer warps + 1 expect_tx arrive), empty[s] (tcgen05.commit)
+//   epilogue      tcgen05.ld -> folded BatchNorm scale/shift, residual add, ReLU/LeakyReLU -> bf16 rows, staged
+//                 through shared memory so that residual loads and output stores are 64-byte coalesced segments
+//
+//   warps  0-3    gather producers (stage ring runs on across tiles, so the next tile's rows are in flight while
+//                 the tensor pipe finishes the current one)
+//          4      TMEM alloc + MMA issuer            5      weight (B) bulk-copy issuer
+//          6-7    kernel-map prefetch: the NEXT tile's 128 x K neighbour rows go global -> registers while the
+//                 current tile runs, then registers -> smem the moment the producers release the buffer
+//          8-11   epilogue (warp w owns TMEM lanes 32 (w-8) ..); overlaps the next tile's gathers
+//
+//   barriers      full[s]  (128 cp.async-completion arrivals + 1 expect_tx)  empty[s]  (tcgen05.commit)
+//                 nbr_full[2] (2 prefetch warps)                     nbr_empty    (4 producer warps)
+//                 kmask_empty[2] (MMA + B issuer)                    tmem_full (commit) / tmem_empty (4 epi warps)
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
-#include <stdlib.h>
 
 #define TC_BM 128
 #define TC_BK 64
 #define TC_A_BYTES (TC_BM * 128)
-#define TC_THREADS 192
-#define TC_LAG 2
+#define TC_THREADS 384
+#define TC_MAX_STAGES 8
 #define TC_MAX_SMEM 232448
+#define TC_MIN_SMEM (120 * 1024)  // more than half an SM: one CTA per SM, so a 512-column TMEM alloc never blocks
+#define TC_STAGE_OUT_BYTES 2048   // per epilogue warp: 32 rows x 64 bytes
 
 struct TcParams {
     const __nv_bfloat16* in1;
@@ -36,11 +48,11 @@ struct TcParams {
     void* out;
     long long V_out;
     int Cin1, Cin2, nchunk1, nchunk2;
-    int K, Cout, n_tile, stages;
+    int Cout, n_tile, n_ntiles, stages;
     int act, out_dtype, tmem_cols;
     float slope;
     unsigned int b_bytes;
-    int debug;  // B2ME_TC_DEBUG (timing experiments only, results invalid): 1 skip gather, 2 skip weights, 4 skip MMA
+    int total_work;  // row tiles x n-tiles
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -75,6 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the executing thread's arrival on `bar` fires when all of its prior cp.async copies have landed (no wait_group)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -115,8 +131,34 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+                 : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
+// KT = kernel volume of the map (27: k3 s1, 8: k2 s2 and its transpose, 1: identity / MinkowskiLinear)
+template <int KT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -124,42 +166,51 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
 
     const int S = p.stages;
     const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
-    const int K = p.K;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
-    // carve: [stages][nbr_s 128*K i32][rows_s 128 i32][scale n_tile][shift n_tile][full S][empty S][tmem_full][tmem_ptr][mask]
+    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 4 x 2 KB][barriers][kmask][tmem ptr]
     uint32_t off = (uint32_t)S * stage_bytes;
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
-    off += TC_BM * K * 4;
-    int32_t* rows_s = reinterpret_cast<int32_t*>(sm + off);  // output row of every tile slot (-1 = past the end)
-    off += TC_BM * 4;
+    off += TC_BM * KT * 4;
     float* scale_s = reinterpret_cast<float*>(sm + off);
-    off += p.n_tile * 4;
+    off += p.Cout * 4;
     float* shift_s = reinterpret_cast<float*>(sm + off);
-    off += p.n_tile * 4;
-    off = (off + 7u) & ~7u;
+    off += p.Cout * 4;
+    off = (off + 15u) & ~15u;
+    const uint32_t stage_out = base + off;
+    off += 4 * TC_STAGE_OUT_BYTES;
     const uint32_t bar_full = base + off;
-    off += 8 * S;
+    off += 8 * TC_MAX_STAGES;
     const uint32_t bar_empty = base + off;
-    off += 8 * S;
-    const uint32_t bar_tmem = base + off;
+    off += 8 * TC_MAX_STAGES;
+    const uint32_t bar_nbr_full = base + off;  // [2]
+    off += 16;
+    const uint32_t bar_nbr_empty = base + off;
     off += 8;
+    const uint32_t bar_kmask_empty = base + off;  // [2]
+    off += 16;
+    const uint32_t bar_tmem_full = base + off;
+    off += 8;
+    const uint32_t bar_tmem_empty = base + off;
+    off += 8;
+    volatile uint32_t* kmask_s = reinterpret_cast<volatile uint32_t*>(sm + off);  // [2 buffers][2 prefetch warps]
+    off += 16;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + off);
-    off += 4;
-    uint32_t* mask_s = reinterpret_cast<uint32_t*>(sm + off);
-
-    const long long row0 = (long long)blockIdx.x * TC_BM;
-    const int n0 = blockIdx.y * p.n_tile;
 
     // ---- one-time setup
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(bar_full + 8 * s, 5);   // 4 producer warps + 1 expect_tx arrive of the B loader
+            mbar_init(bar_full + 8 * s, 129); // 128 producer threads (cp.async-completion arrivals) + the B expect_tx arrive
             mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
         }
-        mbar_init(bar_tmem, 1);
-        *mask_s = 0u;
+        mbar_init(bar_nbr_full, 2);
+        mbar_init(bar_nbr_full + 8, 2);
+        mbar_init(bar_nbr_empty, 4);
+        mbar_init(bar_kmask_empty, 2);
+        mbar_init(bar_kmask_empty + 8, 2);
+        mbar_init(bar_tmem_full, 1);
+        mbar_init(bar_tmem_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -168,152 +219,62 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < TC_BM) {
-        const long long slot = row0 + tid;
-        rows_s[tid] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
-    }
-    __syncthreads();  // mask_s = 0 and rows_s visible
-    {
-        // stage the kernel-map rows of the tile's output rows and find the offsets that occur
-        uint32_t local = 0;
-        if (p.nbr) {
-            const int total = TC_BM * K;
-            for (int i = tid; i < total; i += TC_THREADS) {
-                const int r = i / K;
-                const int row = rows_s[r];
-                const int v = (row >= 0) ? __ldg(p.nbr + (long long)row * K + (i - r * K)) : -1;
-                nbr_s[i] = v;
-                if (v >= 0) local |= 1u << (i - r * K);
-            }
-        } else {
-            local = 1u;
-        }
-        local = __reduce_or_sync(0xffffffffu, local);
-        if (lane == 0 && local) atomicOr(mask_s, local);
-        for (int i = tid; i < p.n_tile; i += TC_THREADS) {
-            scale_s[i] = p.scale ? p.scale[n0 + i] : 1.f;
-            shift_s[i] = p.shift ? p.shift[n0 + i] : 0.f;
-        }
+    for (int i = tid; i < p.Cout; i += TC_THREADS) {
+        scale_s[i] = p.scale ? p.scale[i] : 1.f;
+        shift_s[i] = p.shift ? p.shift[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
-    const uint32_t kmask = *mask_s;
     const int nchunk = p.nchunk1 + p.nchunk2;
+    const int G = gridDim.x;
 
     if (warp < 4) {
         // =============================== gather producers ===============================
         const int j = tid & 7;        // 16-byte piece inside the 128-byte row
         const int rbase = tid >> 3;   // rows rbase + 16*i
-        int issued = 0, arrived = 0;
-        for (int k = 0; k < K; ++k) {
-            if (!((kmask >> k) & 1u)) continue;
-            int idx[8];
+        int ist = 0, iph = 0;         // stage / phase of the next item to issue
+        int it = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
+            const int b = it & 1;
+            mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
+            uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
+            if (!kmask) kmask = 1u;
+#pragma unroll 1
+            for (int k = 0; k < KT; ++k) {
+                if (!((kmask >> k) & 1u)) continue;
+                int idx[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                if (p.nbr) idx[i] = nbr_s[r * K + k];
-                else idx[i] = rows_s[r];
-            }
-            for (int c = 0; c < nchunk; ++c) {
-                const int s = issued % S;
-                if (issued >= S) {
-                    // the slot is free once the MMAs of item (issued - S) have completed. Before blocking on that,
-                    // publish every gather already issued: the MMA warp must never wait for data whose arrival is
-                    // only signalled after a LATER gather could be issued (that would serialise MMA and gather).
-                    const uint32_t par = ((issued / S) & 1) ^ 1;
-                    const bool ready = __all_sync(0xffffffffu, mbar_try_wait(bar_empty + 8 * s, par));
-                    if (!ready) {
-                        if (arrived < issued) {
-                            cp_async_wait<0>();
-                            fence_proxy_async();
-                            __syncwarp();
-                            for (; arrived < issued; ++arrived)
-                                if (lane == 0) mbar_arrive(bar_full + 8 * (arrived % S));
-                        }
-                        mbar_wait(bar_empty + 8 * s, par);
-                    }
-                }
-                const __nv_bfloat16* src;
-                int cin, coff;
-                if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
-                else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * TC_BK; }
-                const int kw = min(TC_BK, cin - coff);
-                if (j * 8 < kw && !(p.debug & 1)) {
-                    const uint32_t a_s = base + (uint32_t)s * stage_bytes;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rbase + 16 * i;
-                        const uint32_t dst = a_s + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-                        const int id = idx[i];
-                        const __nv_bfloat16* g = src + (id >= 0 ? ((long long)id * cin + coff + j * 8) : 0);
-                        cp_async_16(dst, g, id >= 0 ? 16u : 0u);
-                    }
-                }
-                cp_async_commit();
-                ++issued;
-                if (issued - arrived > TC_LAG) {
-                    cp_async_wait<TC_LAG>();
-                    fence_proxy_async();
+                for (int i = 0; i < 8; ++i) idx[i] = nbr_s[(rbase + 16 * i) * KT + k];
+                if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + 8 * (arrived % S));
-                    ++arrived;
+                    if (lane == 0) mbar_arrive(bar_nbr_empty);
                 }
-            }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        __syncwarp();
-        for (; arrived < issued; ++arrived)
-            if (lane == 0) mbar_arrive(bar_full + 8 * (arrived % S));
-
-        // =============================== epilogue ===============================
-        mbar_wait(bar_tmem, 0);
-        tc_fence_after();
-        const long long row = rows_s[tid];
-        const bool row_ok = row >= 0;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int cb = 0; cb < p.n_tile; cb += 16) {
-            uint32_t r[16];
-            if (kmask) {
-                tmem_ld_x16(lane_addr + (uint32_t)cb, r);
-                tmem_ld_wait();
-            } else {
+#pragma unroll 1
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u);
+                    const __nv_bfloat16* src;
+                    int cin, coff;
+                    if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
+                    else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * TC_BK; }
+                    const int kw = min(TC_BK, cin - coff);
+                    if (j * 8 < kw) {
+                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) r[q] = 0u;
-            }
-            if (!row_ok) continue;
-            float v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]) * scale_s[cb + q] + shift_s[cb + q];
-            const long long o = row * p.Cout + n0 + cb;
-            if (p.residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + o);
-                const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-                const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    v[2 * q] += __uint_as_float(w[q] << 16);
-                    v[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rbase + 16 * i;
+                            const uint32_t dst = a_s + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+                            const int id = idx[i];
+                            const __nv_bfloat16* g = src + (id >= 0 ? ((long long)id * cin + coff + j * 8) : 0);
+                            cp_async_16(dst, g, id >= 0 ? 16u : 0u);
+                        }
+                    }
+                    // asynchronous publication: this thread's arrival fires when its copies have landed, so the
+                    // producers run ahead as far as the ring allows and never wait for their own gathers
+                    cp_async_mbar_arrive_noinc(bar_full + 8 * ist);
+                    if (++ist == S) { ist = 0; iph ^= 1; }
                 }
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = apply_act(v[q], p.act, p.slope);
-            if (p.out_dtype == B2ME_BF16) {
-                uint32_t w[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                    w[q] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-                op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                op[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            } else {
-                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
         }
     } else if (warp == 4) {
@@ -322,50 +283,246 @@ __global__ void __launch_bounds__(TC_THREADS) k_spconv_tc(const TcParams p) {
             const int nhalf = p.n_tile > 256 ? 2 : 1;
             const int nh = p.n_tile / nhalf;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nh >> 3) << 17) | (8u << 24);
-            int it = 0;
-            for (int k = 0; k < K; ++k) {
-                if (!((kmask >> k) & 1u)) continue;
-                for (int c = 0; c < nchunk; ++c) {
-                    const int s = it % S;
-                    const int kw = (c < p.nchunk1) ? min(TC_BK, p.Cin1 - c * TC_BK)
-                                                   : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
-                    mbar_wait(bar_full + 8 * s, (it / S) & 1);
+            int st = 0, ph = 0, it = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
+                const int b = it & 1;
+                mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
+                uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
+                if (!kmask) kmask = 1u;
+                if (it > 0) {  // the epilogue of the previous tile must have drained the accumulator
+                    mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u);
                     tc_fence_after();
-                    const uint32_t a_s = base + (uint32_t)s * stage_bytes;
-                    const uint32_t b_s = a_s + TC_A_BYTES;
-                    const uint64_t adesc = make_smem_desc_sw128(a_s);
-                    for (int kk = 0; kk < ((p.debug & 4) ? 0 : kw / 16); ++kk) {
-                        for (int h = 0; h < nhalf; ++h) {
-                            const uint64_t bdesc = make_smem_desc_sw128(b_s + (uint32_t)(h * nh) * 128u);
-                            tc_mma_bf16(tmem_base + (uint32_t)(h * nh), adesc + (uint64_t)(kk * 2),
-                                        bdesc + (uint64_t)(kk * 2), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                        }
-                    }
-                    tc_commit(bar_empty + 8 * s);
-                    ++it;
                 }
+                uint32_t acc = 0u;
+                for (int k = 0; k < KT; ++k) {
+                    if (!((kmask >> k) & 1u)) continue;
+                    for (int c = 0; c < nchunk; ++c) {
+                        const int kw = (c < p.nchunk1) ? min(TC_BK, p.Cin1 - c * TC_BK)
+                                                       : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
+                        mbar_wait(bar_full + 8 * st, (uint32_t)ph);
+                        fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA's async proxy
+                        tc_fence_after();
+                        const uint32_t a_s = base + (uint32_t)st * stage_bytes;
+                        const uint32_t b_s = a_s + TC_A_BYTES;
+                        const uint64_t adesc = make_smem_desc_sw128(a_s);
+                        for (int kk = 0; kk < kw / 16; ++kk) {
+                            for (int h = 0; h < nhalf; ++h) {
+                                const uint64_t bdesc = make_smem_desc_sw128(b_s + (uint32_t)(h * nh) * 128u);
+                                tc_mma_bf16(tmem_base + (uint32_t)(h * nh), adesc + (uint64_t)(kk * 2),
+                                            bdesc + (uint64_t)(kk * 2), idesc, acc);
+                            }
+                            acc = 1u;
+                        }
+                        tc_commit(bar_empty + 8 * st);
+                        if (++st == S) { st = 0; ph ^= 1; }
+                    }
+                }
+                tc_commit(bar_tmem_full);
+                mbar_arrive(bar_kmask_empty + 8 * b);
             }
-            tc_commit(bar_tmem);
         }
-    } else {
+    } else if (warp == 5) {
         // =============================== weight (B) loader ===============================
         if (lane == 0) {
-            int it = 0;
-            for (int k = 0; k < K; ++k) {
-                if (!((kmask >> k) & 1u)) continue;
-                for (int c = 0; c < nchunk; ++c) {
-                    const int s = it % S;
-                    if (it >= S) mbar_wait(bar_empty + 8 * s, ((it / S) & 1) ^ 1);
-                    const uint32_t b_s = base + (uint32_t)s * stage_bytes + TC_A_BYTES;
-                    const uint8_t* g =
-                        p.wpacked + ((size_t)((size_t)blockIdx.y * K + k) * nchunk + c) * (size_t)p.b_bytes;
-                    if (p.debug & 2) {
-                        mbar_arrive(bar_full + 8 * s);
-                    } else {
-                        mbar_arrive_expect_tx(bar_full + 8 * s, p.b_bytes);
-                        bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * s);
+            int st = 0, ph = 0, it = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
+                const int b = it & 1;
+                const int nt = w % p.n_ntiles;
+                mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
+                uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
+                if (!kmask) kmask = 1u;
+                for (int k = 0; k < KT; ++k) {
+                    if (!((kmask >> k) & 1u)) continue;
+                    for (int c = 0; c < nchunk; ++c) {
+                        mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
+                        const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
+                        const uint8_t* g = p.wpacked + ((size_t)((size_t)nt * KT + k) * nchunk + c) * (size_t)p.b_bytes;
+                        mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
+                        bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
+                        if (++st == S) { st = 0; ph ^= 1; }
                     }
-                    ++it;
+                }
+                mbar_arrive(bar_kmask_empty + 8 * b);
+            }
+        }
+    } else if (warp < 8) {
+        // =============================== kernel-map prefetch ===============================
+        // warp wl stages rows 64 wl .. 64 wl + 63 of every tile: 64 x KT entries, 2 KT per lane, held in registers
+        // until the producers have released the (single) smem buffer.
+        const int wl = warp - 6;
+        constexpr int NJ = 2 * KT;
+        int it = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
+            const int b = it & 1;
+            const long long row0 = (long long)(w / p.n_ntiles) * TC_BM + 64 * wl;
+            int rowreg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long slot = row0 + lane + 32 * h;
+                rowreg[h] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
+            }
+            int v[NJ];
+            uint32_t local = 0u;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const int e = lane + 32 * jj;  // < 64 * KT
+                const int rl = e / KT, k = e - rl * KT;
+                const int r0 = __shfl_sync(0xffffffffu, rowreg[0], rl & 31);
+                const int r1 = __shfl_sync(0xffffffffu, rowreg[1], rl & 31);
+                const int row = (rl >> 5) ? r1 : r0;
+                int val;
+                if (p.nbr) val = (row >= 0) ? __ldg(p.nbr + (long long)row * KT + k) : -1;
+                else val = row;
+                v[jj] = val;
+                if (val >= 0) local |= 1u << k;
+            }
+            local = __reduce_or_sync(0xffffffffu, local);
+            if (it >= 1) mbar_wait(bar_nbr_empty, (uint32_t)(it - 1) & 1u);
+            if (it >= 2) mbar_wait(bar_kmask_empty + 8 * b, (uint32_t)((it >> 1) - 1) & 1u);
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) nbr_s[64 * wl * KT + lane + 32 * jj] = v[jj];
+            if (lane == 0) kmask_s[2 * b + wl] = local;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_nbr_full + 8 * b);
+        }
+    } else {
+        // =============================== epilogue ===============================
+        const int we = warp - 8;  // TMEM lanes 32 we .. 32 we + 31  (warp % 4 == we)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(we * 32) << 16);
+        const uint32_t stg = stage_out + (uint32_t)we * TC_STAGE_OUT_BYTES;
+        // staging image: row r (0..31) = 64 bytes, 16-byte piece q stored at q ^ ((r >> 1) & 3): conflict-free for both
+        // the row-per-lane view (lane = row) and the coalesced view (4 lanes per row, 8 rows per access)
+        const uint32_t own = stg + (uint32_t)lane * 64u;
+        const int own_sw = (lane >> 1) & 3;
+        const int crow = lane >> 2, cq = lane & 3;  // coalesced view: rows crow + 8 m, piece cq
+        int it = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
+            const int tile_m = w / p.n_ntiles;
+            const int n0 = (w - tile_m * p.n_ntiles) * p.n_tile;
+            const long long slot = (long long)tile_m * TC_BM + we * 32 + lane;
+            const int row = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
+            int crows[4];  // output rows of the coalesced view
+#pragma unroll
+            for (int m = 0; m < 4; ++m) crows[m] = __shfl_sync(0xffffffffu, row, crow + 8 * m);
+
+            if (p.out_dtype == B2ME_BF16) {
+                const __nv_bfloat16* resp = p.residual;
+                __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+                uint4 R[4];
+                auto load_res = [&](int cb) {  // coalesced: 64-byte segment of 8 rows per access
+                    const int cw = min(32, p.n_tile - cb);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        R[m] = make_uint4(0u, 0u, 0u, 0u);
+                        if (crows[m] >= 0 && cq * 8 < cw)
+                            R[m] = __ldg(reinterpret_cast<const uint4*>(resp + (long long)crows[m] * p.Cout + n0 + cb +
+                                                                        cq * 8));
+                    }
+                };
+                if (resp) load_res(0);
+                mbar_wait(bar_tmem_full, (uint32_t)it & 1u);
+                tc_fence_after();
+                for (int cb = 0; cb < p.n_tile; cb += 32) {
+                    const int cw = min(32, p.n_tile - cb);
+                    uint32_t r[32];
+                    if (cw == 32) {
+                        tmem_ld_x32(lane_addr + (uint32_t)cb, r);
+                    } else {
+                        tmem_ld_x16(lane_addr + (uint32_t)cb, r);
+#pragma unroll
+                        for (int q = 16; q < 32; ++q) r[q] = 0u;
+                    }
+                    if (resp) {
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int rr = crow + 8 * m;
+                            st_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4), R[m]);
+                        }
+                        __syncwarp();
+                        if (cb + 32 < p.n_tile) load_res(cb + 32);  // in flight during this chunk's math and stores
+                    }
+                    tmem_ld_wait();
+                    if (cb + 32 >= p.n_tile) {  // accumulator fully read: the next tile's MMAs may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tmem_empty);
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int col = min(n0 + cb + q, p.Cout - 1);
+                        v[q] = __uint_as_float(r[q]) * scale_s[col] + shift_s[col];
+                    }
+                    if (resp) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 a = ld_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4));
+                            const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
+                                v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+                            }
+                        }
+                        __syncwarp();  // every lane has read its residual row before the buffer takes the outputs
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = apply_act(v[q4 * 8 + 2 * e], p.act, p.slope);
+                            const float x1 = apply_act(v[q4 * 8 + 2 * e + 1], p.act, p.slope);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int rr = crow + 8 * m;
+                        const uint4 o = ld_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4));
+                        if (crows[m] >= 0 && cq * 8 < cw)
+                            *reinterpret_cast<uint4*>(outp + (long long)crows[m] * p.Cout + n0 + cb + cq * 8) = o;
+                    }
+                    __syncwarp();  // staging is reused by the next chunk
+                }
+            } else {
+                // fp32 rows (parity tests only): row-per-lane stores
+                mbar_wait(bar_tmem_full, (uint32_t)it & 1u);
+                tc_fence_after();
+                for (int cb = 0; cb < p.n_tile; cb += 16) {
+                    uint32_t r[16];
+                    tmem_ld_x16(lane_addr + (uint32_t)cb, r);
+                    tmem_ld_wait();
+                    if (cb + 16 >= p.n_tile) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tmem_empty);
+                    }
+                    if (row < 0) continue;
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        v[q] = __uint_as_float(r[q]) * scale_s[n0 + cb + q] + shift_s[n0 + cb + q];
+                    const long long o = (long long)row * p.Cout + n0 + cb;
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + o);
+                        const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                        const uint32_t wv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            v[2 * q] += __uint_as_float(wv[q] << 16);
+                            v[2 * q + 1] += __uint_as_float(wv[q] & 0xFFFF0000u);
+                        }
+                    }
+                    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        op[q] = make_float4(apply_act(v[4 * q], p.act, p.slope), apply_act(v[4 * q + 1], p.act, p.slope),
+                                            apply_act(v[4 * q + 2], p.act, p.slope),
+                                            apply_act(v[4 * q + 3], p.act, p.slope));
                 }
             }
         }
@@ -386,7 +543,7 @@ static int tc_n_tile(int Cout) {
 }
 
 extern "C" int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout) {
-    if (K < 1 || K > 32 || Cin1 < 16 || Cin2 < 0 || Cout < 16) return 0;
+    if ((K != 1 && K != 8 && K != 27) || Cin1 < 16 || Cin2 < 0 || Cout < 16 || Cout > 1024) return 0;
     if (Cin1 % 16 || Cin2 % 16 || Cout % 16) return 0;
     const int nt = tc_n_tile(Cout);
     if (Cout % nt) return 0;
@@ -448,6 +605,34 @@ extern "C" int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, i
     return B2ME_OK;
 }
 
+static int tc_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+        else
+            sms = B2ME_NUM_SMS;
+    }
+    return sms;
+}
+
+template <int KT>
+static int tc_launch(const TcParams& p, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_spconv_tc<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) !=
+            cudaSuccess)
+            return B2ME_ELAUNCH;
+        attr_set = true;
+    }
+    const int grid = p.total_work < tc_num_sms() ? p.total_work : tc_num_sms();
+    k_spconv_tc<KT><<<grid, TC_THREADS, smem, stream>>>(p);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
 extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, const void* packed_w,
                                   const int32_t* nbr, const int32_t* perm, int K, int64_t V_out, int Cout,
                                   const float* scale, const float* shift, const void* residual, int act, float slope,
@@ -474,37 +659,33 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.Cin2 = Cin2;
     p.nchunk1 = (Cin1 + TC_BK - 1) / TC_BK;
     p.nchunk2 = (Cin2 + TC_BK - 1) / TC_BK;
-    p.K = K;
     p.Cout = Cout;
     p.n_tile = tc_n_tile(Cout);
+    p.n_ntiles = Cout / p.n_tile;
     p.act = act;
     p.out_dtype = out_dtype;
     p.slope = slope;
     p.b_bytes = (unsigned)p.n_tile * 128u;
-    {
-        const char* dbg = getenv("B2ME_TC_DEBUG");
-        p.debug = dbg ? atoi(dbg) : 0;
-    }
     int cols = 32;
     while (cols < p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
+    const int64_t work = ceil_div64(V_out, TC_BM) * p.n_ntiles;
+    if (work > 0x7fffffff) return B2ME_EUNSUPPORTED;
+    p.total_work = (int)work;
 
-    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * (K + 1) * 4 + (size_t)p.n_tile * 8 + 8 + 16 * 8 + 64;
+    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + (size_t)Cout * 8 + 16 +
+                         4 * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 16 + 8 + 16 + 8 + 8 + 16 + 16;
     const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
-    int S = 4;
+    int S = TC_MAX_STAGES;
     while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
     if (S < 3) return B2ME_EUNSUPPORTED;
     p.stages = S;
-    const size_t smem = fixed + (size_t)S * stage_bytes;
+    size_t smem = fixed + (size_t)S * stage_bytes;
+    if (smem < TC_MIN_SMEM) smem = TC_MIN_SMEM;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_spconv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess)
-            return B2ME_ELAUNCH;
-        attr_set = true;
-    }
-    dim3 grid((unsigned)ceil_div64(V_out, TC_BM), (unsigned)(Cout / p.n_tile));
-    k_spconv_tc<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    B2ME_CHECK_LAUNCH();
-    return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (K == 27) return tc_launch<27>(p, smem, s);
+    if (K == 8) return tc_launch<8>(p, smem, s);
+    if (K == 1) return tc_launch<1>(p, smem, s);
+    return B2ME_EUNSUPPORTED;
 }

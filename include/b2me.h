@@ -229,7 +229,7 @@ int b2me_kabsch_batched(const double* ref, const double* tgt, const int32_t* npa
  *   init_T [F,16] f64 row-major 4x4; out_T [F,16] f64; out_stats [F,4] f64 = fitness, inlier_rmse,
  *   iterations run, #correspondences
  * ---------------------------------------------------------------------------------------------- */
-size_t b2me_icp_workspace_bytes(int64_t T_total, int F);
+size_t b2me_icp_workspace_bytes(int64_t T_total, int F, int S);
 int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                          const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
                          double max_corr, int max_iter, double rel_fitness, double rel_rmse,

@@ -205,12 +205,15 @@ def linear_forward(module, x: SparseTensor):
         F = x._materialize()
         V = F.shape[0]
         out = torch.empty((V, Cout), dtype=torch.float32, device=F.device)
+        amax = torch.empty((max(V, 1),), dtype=torch.uint8, device=F.device)
         Wt = lin.weight.detach().float().contiguous()
         b = lin.bias.detach().float().contiguous() if lin.bias is not None else None
-        check(lib.b2me_linear_small(ptr(F), dtype_code(F.dtype), V, F.shape[1], ptr(Wt), ptr(b), Cout, ptr(out), None,
-                                    stream()), "linear_small")
+        check(lib.b2me_linear_small(ptr(F), dtype_code(F.dtype), V, F.shape[1], ptr(Wt), ptr(b), Cout, ptr(out),
+                                    ptr(amax), stream()), "linear_small")
         _count(1)
-        return x._child(features=out)
+        res = x._child(features=out)
+        res._row_argmax = amax[:V]  # per-voxel arg-max of the logits (lowest index wins ties), free by-product
+        return res
     p = _Pending("conv", _sources(x), module=module, nbr=None, K=1, V_out=x.num_rows, Cout=Cout)
     if lin.bias is not None:
         p.shift = lin.bias.detach().float().contiguous()

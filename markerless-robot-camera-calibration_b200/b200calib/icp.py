@@ -113,7 +113,7 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
     init_T = init_T.to(dev, torch.float64).contiguous().view(F, 16)
     out_T = torch.empty((F, 16), dtype=torch.float64, device=dev)
     stats = torch.empty((F, 4), dtype=torch.float64, device=dev)
-    ws = torch.empty((lib.b2me_icp_workspace_bytes(targets.shape[0], F),), dtype=torch.uint8, device=dev)
+    ws = torch.empty((lib.b2me_icp_workspace_bytes(targets.shape[0], F, source.shape[0]),), dtype=torch.uint8, device=dev)
     check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
                                    ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")

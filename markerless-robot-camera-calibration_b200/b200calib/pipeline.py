@@ -107,11 +107,14 @@ def segment_points(model, points, rgb, bidx, nb, scale):
     out = model(sp)
     logits = out.F  # [V, C] f32 voxel logits (K5)
     V, C = logits.shape
-    vlab = torch.empty((max(V, 1),), dtype=torch.uint8, device=logits.device)
-    # slice + arg-max fused: arg-max per voxel, then 1 byte per point through the inverse map
-    check(lib.b2me_linear_small(ptr(logits), 0, V, C, ptr(_eye(C, logits.device)), None, C, None, ptr(vlab), stream()),
-          "argmax")
-    _count(1)
+    # slice + arg-max fused: arg-max per voxel (by-product of the head's last linear), then 1 byte per point
+    # through the inverse map
+    vlab = getattr(out, "_row_argmax", None)
+    if vlab is None:
+        vlab = torch.empty((max(V, 1),), dtype=torch.uint8, device=logits.device)
+        check(lib.b2me_linear_small(ptr(logits), 0, V, C, ptr(_eye(C, logits.device)), None, C, None, ptr(vlab),
+                                    stream()), "argmax")
+        _count(1)
     N = points.shape[0]
     labels = torch.empty((max(N, 1),), dtype=torch.uint8, device=logits.device)
     check(lib.b2me_gather_labels(ptr(vlab), ptr(fld.inverse_mapping), N, ptr(labels), stream()), "gather_labels")

@@ -1,10 +1,18 @@
 // cluster.cu — K7: largest single-linkage cluster per segment (utils/output.py:13-28) as connected
-// components of {d(i,j) < dist} on a uniform grid of cell size `dist`, with a lock-free union-find.
+// components of {d(i,j) < dist} with a lock-free union-find over a uniform grid of cell size 0.57 dist:
+//   * the diagonal of a cell is 0.987 dist < dist, so all points of one cell are in one component: one union per
+//     point with its cell's representative, no distance tests;
+//   * two cells can only be linked when they are at most 2 cells apart per axis (a gap of 2 cells is 1.14 dist):
+//     one warp per (cell, neighbour cell) pair skips pairs that are already in one component and otherwise tests
+//     point pairs (fp64, the reference's threshold test) until the first one within dist.
+// Exactly the components of the full graph, in O(n) distance tests for a dense blob instead of O(n^2).
 //
 // Determinism: unions always hook the larger root under the smaller one, so after flattening a
 // component's label is its lowest point index whatever the thread interleaving; component sizes are
 // integer atomics; the winner is max(size) with ties to the lowest label.
 #include "common.cuh"
+
+#define CLUSTER_CELL_FRAC 0.57  // cell edge / dist; sqrt(3) * 0.57 = 0.987 < 1
 
 // from coords.cu (same translation unit set; declared here)
 extern "C" int b2me_quantize_unique(const float*, const int32_t*, int64_t, const float*, int, int, int32_t*, float*,
@@ -76,9 +84,10 @@ __global__ void k_cluster_cells(const float* __restrict__ pts, const int32_t* __
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int seg = seg_of_row(seg_offsets, S, (int)i);
-    const int cx = (int)floor((double)pts[i * 3 + 0] / dist);
-    const int cy = (int)floor((double)pts[i * 3 + 1] / dist);
-    const int cz = (int)floor((double)pts[i * 3 + 2] / dist);
+    const double cs = dist * CLUSTER_CELL_FRAC;
+    const int cx = (int)floor((double)pts[i * 3 + 0] / cs);
+    const int cy = (int)floor((double)pts[i * 3 + 1] / cs);
+    const int cz = (int)floor((double)pts[i * 3 + 2] / cs);
     cellq[i] = make_int4(seg, cx, cy, cz);
     parent[i] = (int32_t)i;
     comp_size[i] = 0;
@@ -124,33 +133,61 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_cluster_link(const float* __restrict__ pts, const int4* __restrict__ cellq, int64_t n,
-               const HashSlot* __restrict__ tab, unsigned long long mask, const int32_t* __restrict__ cell_start,
-               const int32_t* __restrict__ sorted, double dist2, int32_t* __restrict__ parent) {
+// every point joins the representative (first sorted member) of its cell
+__global__ void k_cluster_intra(const int32_t* __restrict__ cell_of, int64_t n, const int32_t* __restrict__ cell_start,
+                                const int32_t* __restrict__ sorted, int32_t* __restrict__ parent) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int4 c = cellq[i];
-    if (!coord_in_range(c.x, c.y, c.z, c.w)) return;
-    const double xi = pts[i * 3], yi = pts[i * 3 + 1], zi = pts[i * 3 + 2];
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = c.y + dx, y = c.z + dy, z = c.w + dz;
-                if (!coord_in_range(c.x, x, y, z)) continue;
-                const unsigned int cid = table_lookup(tab, mask, pack_key(c.x, x, y, z));
-                if (cid == 0xFFFFFFFFu) continue;
-                const int s0 = cell_start[cid], s1 = cell_start[cid + 1];
-                for (int s = s0; s < s1; ++s) {
-                    const int j = sorted[s];
-                    if (j >= i) continue;  // each unordered pair once
+    const int c = cell_of[i];
+    if (c < 0) return;
+    const int rep = sorted[cell_start[c]];
+    if (rep != (int)i) uf_union(parent, (int)i, rep);
+}
+
+// one warp per (cell a, neighbour offset in the positive half space, |d| <= reach): link the two cells when any
+// point pair is within dist. Pairs already in one component are skipped, so the second pass (reach 2) only tests
+// pairs of cells that the first pass (reach 1) left in different components.
+__global__ void __launch_bounds__(256)
+k_cluster_inter(const float* __restrict__ pts, const int32_t* __restrict__ cell_coords, const int32_t* __restrict__ ncells_p,
+                const HashSlot* __restrict__ tab, unsigned long long mask, const int32_t* __restrict__ cell_start,
+                const int32_t* __restrict__ sorted, double dist2, int reach, int32_t* __restrict__ parent) {
+    const int ncells = *ncells_p;
+    const int side = 2 * reach + 1;
+    const int noff = (side * side * side) / 2;  // offsets after the centre in (dz, dy, dx) lexicographic order
+    const long long ntask = (long long)ncells * noff;
+    const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntask; t += wstride) {
+        const int a = (int)(t / noff);
+        const int o = (int)(t - (long long)a * noff) + noff + 1;  // index in the side^3 cube, strictly after the centre
+        const int dx = o % side - reach, dy = (o / side) % side - reach, dz = o / (side * side) - reach;
+        const int4 ca = *reinterpret_cast<const int4*>(cell_coords + 4 * (long long)a);
+        const int x = ca.y + dx, y = ca.z + dy, z = ca.w + dz;
+        if (!coord_in_range(ca.x, x, y, z)) continue;
+        const unsigned int b = table_lookup(tab, mask, pack_key(ca.x, x, y, z));
+        if (b == 0xFFFFFFFFu) continue;
+        const int a0 = cell_start[a], a1 = cell_start[a + 1], b0 = cell_start[b], b1 = cell_start[b + 1];
+        const int repa = sorted[a0], repb = sorted[b0];
+        if (uf_find(parent, repa) == uf_find(parent, repb)) continue;  // warp-uniform
+        bool linked = false;
+        for (int ia = a0; ia < a1 && !linked; ++ia) {
+            const int i = sorted[ia];
+            const double xi = pts[(int64_t)i * 3], yi = pts[(int64_t)i * 3 + 1], zi = pts[(int64_t)i * 3 + 2];
+            for (int jb = b0; jb < b1; jb += 32) {
+                bool hit = false;
+                if (jb + lane < b1) {
+                    const int j = sorted[jb + lane];
                     const double ddx = xi - (double)pts[(int64_t)j * 3];
                     const double ddy = yi - (double)pts[(int64_t)j * 3 + 1];
                     const double ddz = zi - (double)pts[(int64_t)j * 3 + 2];
-                    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                    if (d2 < dist2) uf_union(parent, (int)i, j);
+                    hit = (ddx * ddx + ddy * ddy + ddz * ddz) < dist2;
                 }
+                if (__any_sync(0xffffffffu, hit)) { linked = true; break; }
             }
+        }
+        if (linked && lane == 0) uf_union(parent, repa, repb);
+        __syncwarp();
+    }
 }
 
 __global__ void k_cluster_flatten(int32_t* __restrict__ parent, int64_t n, int32_t* __restrict__ comp_size) {
@@ -226,9 +263,11 @@ extern "C" int b2me_largest_cluster(const float* points_xyz, const int32_t* seg_
         if (rc != B2ME_OK) return rc;
         k_cell_fill<<<G, T, 0, s>>>(w.cell_of, n, w.cell_start, w.cursor, w.sorted);
         const unsigned long long mask = (unsigned long long)(b2me_table_slots(n) - 1);
-        k_cluster_link<<<(unsigned)ceil_div64(n, 128), 128, 0, s>>>(points_xyz, w.cellq, n,
-                                                                     reinterpret_cast<const HashSlot*>(w.table), mask,
-                                                                     w.cell_start, w.sorted, dist * dist, w.parent);
+        k_cluster_intra<<<G, T, 0, s>>>(w.cell_of, n, w.cell_start, w.sorted, w.parent);
+        for (int reach = 1; reach <= 2; ++reach)
+            k_cluster_inter<<<B2ME_NUM_SMS * 4, 256, 0, s>>>(points_xyz, w.cell_coords, w.counts,
+                                                             reinterpret_cast<const HashSlot*>(w.table), mask,
+                                                             w.cell_start, w.sorted, dist * dist, reach, w.parent);
         k_cluster_flatten<<<G, T, 0, s>>>(w.parent, n, w.comp_size);
         k_cluster_root<<<G, T, 0, s>>>(w.parent, n, w.cursor);  // cursor reused as root[]
         k_cluster_best<<<G, T, 0, s>>>(w.comp_size, seg_offsets, S, n, w.best);

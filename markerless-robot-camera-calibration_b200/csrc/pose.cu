@@ -166,10 +166,11 @@ struct IcpWs {
     int32_t* cell_cursor;  // [F, ICP_CELLS]
     double* partial;       // [F, ICP_MAX_CHUNKS, ICP_NSUM]
     float4* sorted;        // [T_total] xyz + original index bits
+    int32_t* match;        // [F, S] position (in `sorted`, frame-relative) of the last match of every source point
     size_t total;
 };
 
-static IcpWs carve_icp_ws(void* ws, int64_t T_total, int F) {
+static IcpWs carve_icp_ws(void* ws, int64_t T_total, int F, int S) {
     IcpWs w;
     char* base = reinterpret_cast<char*>(ws);
     size_t off = 0;
@@ -185,11 +186,14 @@ static IcpWs carve_icp_ws(void* ws, int64_t T_total, int F) {
     w.cell_cursor = reinterpret_cast<int32_t*>(take((size_t)F1 * ICP_CELLS * 4));
     w.partial = reinterpret_cast<double*>(take((size_t)F1 * ICP_MAX_CHUNKS * ICP_NSUM * sizeof(double)));
     w.sorted = reinterpret_cast<float4*>(take((size_t)(T_total > 0 ? T_total : 1) * sizeof(float4)));
+    w.match = reinterpret_cast<int32_t*>(take((size_t)F1 * (size_t)(S > 0 ? S : 1) * 4));
     w.total = off;
     return w;
 }
 
-extern "C" size_t b2me_icp_workspace_bytes(int64_t T_total, int F) { return carve_icp_ws(nullptr, T_total, F).total; }
+extern "C" size_t b2me_icp_workspace_bytes(int64_t T_total, int F, int S) {
+    return carve_icp_ws(nullptr, T_total, F, S).total;
+}
 
 __device__ __forceinline__ int icp_cell_coord(double v, double origin, double inv_h, int dim) {
     int c = (int)floor((v - origin) * inv_h);
@@ -354,75 +358,82 @@ __device__ __noinline__ void icp_frame_update(IcpState* st, const double* tot, c
     }
 }
 
-// grid (nchunk, F). Evaluation `ev` of every frame that has not converged yet.
-// dynamic smem: [cell offsets ICP_CELLS+1 i32][target points of the frame, float4, when they fit (tcap points)]
+// Exact nearest target of (px,py,pz) within sqrt(R2): every grid cell that intersects the sphere of radius sqrt(best)
+// around the query is scanned, and `best` shrinks as candidates are found. z planes and y rows are visited centre-out
+// and pruned by their slab distance; inside a row the cells that can still hold a closer point form ONE contiguous x
+// range, i.e. one contiguous run of the cell-sorted target array (x is the fastest cell index).
+// `seed` = position of this source point's match in the previous iteration (or -1): the pose moves little between
+// iterations, so the seed's distance is a tight bound and only a thin shell of candidates is touched.
+#define ICP_LB_SLACK 1e-9  // metres: absorbs the rounding of the cell assignment at cell faces
+__device__ __forceinline__ double icp_slab_dist(double v, double lo, double h) {
+    const double a = lo - v, b = v - (lo + h);
+    double d = a > b ? a : b;
+    d -= ICP_LB_SLACK;
+    return d > 0.0 ? d : 0.0;
+}
+
 template <bool kSmemTargets>
 __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const int* cs, const IcpFrameGrid& g,
-                                           double px, double py, double pz, double R2, double& best, int& best_j,
-                                           double& bx, double& by, double& bz) {
-    const int cx = icp_cell_coord(px, g.origin[0], g.inv_h, g.dims[0]);
-    const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
-    const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
-    // m = distance from the query to the nearest face of its own cell that has cells behind it: every point of
-    // ring r (Chebyshev cell distance r >= 1) is at least m + (r-1) h away.
-    double m = 1e300;
-    {
-        const double lx = px - (g.origin[0] + cx * g.h), ly = py - (g.origin[1] + cy * g.h),
-                     lz = pz - (g.origin[2] + cz * g.h);
-        if (cx > 0) m = fmin(m, lx);
-        if (cx < g.dims[0] - 1) m = fmin(m, g.h - lx);
-        if (cy > 0) m = fmin(m, ly);
-        if (cy < g.dims[1] - 1) m = fmin(m, g.h - ly);
-        if (cz > 0) m = fmin(m, lz);
-        if (cz < g.dims[2] - 1) m = fmin(m, g.h - lz);
-        if (m < 0.0) m = 0.0;
-    }
+                                           double px, double py, double pz, double R2, int seed, double& best,
+                                           int& best_j, int& best_s, double& bx, double& by, double& bz) {
     best = R2;  // strict '<' below: only neighbours inside the radius qualify
     best_j = 0x7FFFFFFF;
-    for (int r = 0; r <= ICP_GRID; ++r) {
-        if (r >= 1) {
-            const double lb = m + (double)(r - 1) * g.h;
-            if (lb * lb >= best) break;
+    best_s = -1;
+    auto consider = [&](int s) {
+        float4 q;
+        if (kSmemTargets) q = tg[s];
+        else q = __ldg(tg + s);
+        const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const int j = __float_as_int(q.w);
+        if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
+            best = d2; best_j = j; best_s = s; bx = q.x; by = q.y; bz = q.z;
         }
-        const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
-        if (z0 < 0 && y0 < 0 && x0 < 0 && z1 >= g.dims[2] && y1 >= g.dims[1] && x1 >= g.dims[0]) break;
-        for (int z = max(z0, 0); z <= min(z1, g.dims[2] - 1); ++z) {
-            const bool zf = (z == z0 || z == z1);
-            for (int y = max(y0, 0); y <= min(y1, g.dims[1] - 1); ++y) {
-                const bool yf = (y == y0 || y == y1);
-                const int xstep = (zf || yf || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
-                for (int x = x0; x <= x1; x += xstep) {
-                    if (x < 0 || x >= g.dims[0]) continue;
-                    const int cell = (z * g.dims[1] + y) * g.dims[0] + x;
-                    const int s0 = cs[cell], s1 = cs[cell + 1];
-                    for (int s = s0; s < s1; ++s) {
-                        float4 q;
-                        if (kSmemTargets) q = tg[s];
-                        else q = __ldg(tg + s);
-                        const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        const int j = __float_as_int(q.w);
-                        if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
-                            best = d2; best_j = j; bx = q.x; by = q.y; bz = q.z;
-                        }
-                    }
-                }
-            }
+    };
+    if (seed >= 0) consider(seed);
+    const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = icp_cell_coord(pz, g.origin[2], g.inv_h, g.dims[2]);
+    // planes / rows farther than `reach` cells from the query's (clamped) cell cannot intersect the sphere
+    const int reach = (int)(sqrt(best) * g.inv_h) + 2;
+    const int zspan = min(max(cz, g.dims[2] - 1 - cz), reach), yspan = min(max(cy, g.dims[1] - 1 - cy), reach);
+    for (int kz = 0; kz <= 2 * zspan; ++kz) {
+        const int z = cz + ((kz & 1) ? -((kz + 1) >> 1) : (kz >> 1));
+        if (z < 0 || z >= g.dims[2]) continue;
+        const double dz = icp_slab_dist(pz, g.origin[2] + z * g.h, g.h);
+        const double dz2 = dz * dz;
+        if (dz2 >= best) continue;
+        for (int ky = 0; ky <= 2 * yspan; ++ky) {
+            const int y = cy + ((ky & 1) ? -((ky + 1) >> 1) : (ky >> 1));
+            if (y < 0 || y >= g.dims[1]) continue;
+            const double dy = icp_slab_dist(py, g.origin[1] + y * g.h, g.h);
+            const double rem = best - dz2 - dy * dy;
+            if (rem <= 0.0) continue;
+            const double rx = sqrt(rem) + ICP_LB_SLACK;
+            int x0 = (int)floor((px - rx - g.origin[0]) * g.inv_h);
+            int x1 = (int)floor((px + rx - g.origin[0]) * g.inv_h);
+            if (x0 < 0) x0 = 0;
+            if (x1 > g.dims[0] - 1) x1 = g.dims[0] - 1;
+            if (x0 > x1) continue;
+            const int row = (z * g.dims[1] + y) * g.dims[0];
+            const int s0 = cs[row + x0], s1 = cs[row + x1 + 1];
+            for (int s = s0; s < s1; ++s) consider(s);
         }
     }
 }
 
-__global__ void __launch_bounds__(ICP_THREADS)
+#define ICP_EVAL_THREADS 512
+__global__ void __launch_bounds__(ICP_EVAL_THREADS)
 k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
            const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
-           const float4* __restrict__ sorted, IcpState* __restrict__ state, double* __restrict__ partial_all,
+           const float4* __restrict__ sorted, int32_t* __restrict__ match_all, IcpState* __restrict__ state,
+           double* __restrict__ partial_all,
            int ev, int tcap, double max_corr, int max_iter, double rel_fitness, double rel_rmse,
            double* __restrict__ out_T, double* __restrict__ out_stats) {
     extern __shared__ __align__(16) unsigned char icp_smem[];
     float4* tg_s = reinterpret_cast<float4*>(icp_smem);
     int* cs = reinterpret_cast<int*>(icp_smem + (size_t)tcap * sizeof(float4));
     __shared__ double T_s[12];
-    __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
+    __shared__ double red[ICP_EVAL_THREADS / 32][ICP_NSUM];
     __shared__ double tot[ICP_NSUM];
     __shared__ IcpFrameGrid g;
     __shared__ int last_s;
@@ -449,15 +460,18 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
 #pragma unroll
     for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
     if (nT > 0) {
-        for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < S; i += nchunk * ICP_THREADS) {
+        int32_t* match = match_all + (int64_t)f * S;
+        for (int i = blockIdx.x * ICP_EVAL_THREADS + threadIdx.x; i < S; i += nchunk * ICP_EVAL_THREADS) {
             const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
             const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
             const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
             const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
             double best, bx = 0, by = 0, bz = 0;
-            int best_j;
-            if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, best, best_j, bx, by, bz);
-            else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, best, best_j, bx, by, bz);
+            int best_j, best_s;
+            const int seed = ev > 0 ? match[i] : -1;
+            if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+            else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+            match[i] = best_s;
             if (best_j != 0x7FFFFFFF) {
                 acc[0] += 1.0; acc[1] += best;
                 acc[2] += px; acc[3] += py; acc[4] += pz;
@@ -479,7 +493,7 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
     double* partial = partial_all + (int64_t)f * ICP_MAX_CHUNKS * ICP_NSUM;
     if (threadIdx.x < ICP_NSUM) {
         double v = 0.0;
-        for (int wv = 0; wv < ICP_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        for (int wv = 0; wv < ICP_EVAL_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
         partial[blockIdx.x * ICP_NSUM + threadIdx.x] = v;
         __threadfence();
     }
@@ -502,7 +516,7 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
         icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
 }
 
-#define ICP_SMEM_TARGETS 4096
+#define ICP_EVAL_SMEM (200 * 1024)  // dynamic smem of k_icp_eval: cell offsets + as many target points as fit
 
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
@@ -513,16 +527,16 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
     if (F == 0) return B2ME_OK;
     if (F > 65535) return B2ME_EUNSUPPORTED;  // gridDim.y
-    IcpWs w = carve_icp_ws(ws, T_total, F);
+    IcpWs w = carve_icp_ws(ws, T_total, F, S);
     if (ws_bytes < w.total) return B2ME_EWORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     k_icp_build_grid<<<(unsigned)F, ICP_THREADS, 0, s>>>(target_xyz, tgt_offsets, init_T, w.grids, w.state,
                                                          w.cell_start, w.cell_cursor, w.sorted);
-    int nchunk = (S + ICP_THREADS - 1) / ICP_THREADS;
+    int nchunk = (S + ICP_EVAL_THREADS - 1) / ICP_EVAL_THREADS;
     if (nchunk > ICP_MAX_CHUNKS) nchunk = ICP_MAX_CHUNKS;
     const dim3 grid((unsigned)nchunk, (unsigned)F);
-    const int tcap = ICP_SMEM_TARGETS;
-    const size_t smem = (size_t)tcap * sizeof(float4) + (size_t)(ICP_CELLS + 1) * sizeof(int);
+    const size_t smem = ICP_EVAL_SMEM;
+    const int tcap = (int)((smem - (size_t)(ICP_CELLS + 1) * sizeof(int)) / sizeof(float4));
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_icp_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -531,9 +545,9 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     }
     // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
     for (int ev = 0; ev <= max_iter; ++ev)
-        k_icp_eval<<<grid, ICP_THREADS, smem, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted, w.state,
-                                                   w.partial, ev, tcap, max_corr, max_iter, rel_fitness, rel_rmse,
-                                                   out_T, out_stats);
+        k_icp_eval<<<grid, ICP_EVAL_THREADS, smem, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted,
+                                                        w.match, w.state, w.partial, ev, tcap, max_corr, max_iter,
+                                                        rel_fitness, rel_rmse, out_T, out_stats);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -207,6 +207,107 @@ k_linear_small(const void* __restrict__ in, int in_dtype, int64_t V, int Cin, co
     }
 }
 
+// Vectorised variant for the head (Cin = 1024 bf16 / f32 rows): a warp takes LS_ROWS rows at a time, every lane reads
+// 16 bytes of each row per step (the warp covers 512 contiguous bytes), the weights come from shared memory once per
+// step for all LS_ROWS rows. HBM-bound: V * Cin * e bytes in, V * (4 Cout + 1) out.
+#define LS_ROWS 4
+template <int CO, bool BF16>
+__global__ void __launch_bounds__(256)
+k_linear_small_vec(const void* __restrict__ in, int64_t V, int Cin, const float* __restrict__ Wt,
+                   const float* __restrict__ bias, float* __restrict__ out_logits, uint8_t* __restrict__ out_argmax) {
+    extern __shared__ float w_s[];  // [CO][Cin]
+    for (int i = threadIdx.x; i < CO * Cin; i += blockDim.x) w_s[i] = Wt[i];
+    __syncthreads();
+    constexpr int VEC = BF16 ? 8 : 4;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t ngroups = (V + LS_ROWS - 1) / LS_ROWS;
+    for (int64_t grp = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); grp < ngroups;
+         grp += (int64_t)gridDim.x * warps_per_block) {
+        const int64_t row0 = grp * LS_ROWS;
+        float acc[LS_ROWS][CO];
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+            for (int o = 0; o < CO; ++o) acc[r][o] = 0.f;
+        for (int c = lane * VEC; c < Cin; c += 32 * VEC) {
+            float x[LS_ROWS][VEC];
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r) {
+                const int64_t row = row0 + r < V ? row0 + r : V - 1;  // clamped: the tail rows are not stored
+                if (BF16) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const __nv_bfloat16*>(in) + row * Cin + c));
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        x[r][2 * e] = __uint_as_float(wv[e] << 16);
+                        x[r][2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u);
+                    }
+                } else {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) +
+                                                                           row * Cin + c));
+                    x[r][0] = v.x; x[r][1] = v.y; x[r][2] = v.z; x[r][3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < CO; ++o) {
+                float w[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; e += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(w_s + o * Cin + c + e);
+                    w[e] = t.x; w[e + 1] = t.y; w[e + 2] = t.z; w[e + 3] = t.w;
+                }
+#pragma unroll
+                for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[r][o] = fmaf(x[r][e], w[e], acc[r][o]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+            for (int o = 0; o < CO; ++o)
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc[r][o] += __shfl_xor_sync(0xffffffffu, acc[r][o], s);
+        if (lane < LS_ROWS && row0 + lane < V) {
+            const int64_t row = row0 + lane;
+            float best = -INFINITY;
+            int besti = 0;
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r) {
+                if (r != lane) continue;
+#pragma unroll
+                for (int o = 0; o < CO; ++o) {
+                    const float v = acc[r][o] + (bias ? bias[o] : 0.f);
+                    if (out_logits) out_logits[row * CO + o] = v;
+                    if (v > best) {  // strict: lowest index wins ties
+                        best = v;
+                        besti = o;
+                    }
+                }
+            }
+            if (out_argmax) out_argmax[row] = (uint8_t)besti;
+        }
+    }
+}
+
+template <int CO>
+static void launch_linear_small_vec(const void* in, int in_dtype, int64_t V, int Cin, const float* Wt, const float* bias,
+                                    float* out_logits, uint8_t* out_argmax, size_t smem, cudaStream_t s) {
+    int64_t blocks = ceil_div64(ceil_div64(V, LS_ROWS), 8);
+    if (blocks > B2ME_NUM_SMS * 4) blocks = B2ME_NUM_SMS * 4;
+    if (in_dtype == B2ME_BF16) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_linear_small_vec<CO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_linear_small_vec<CO, true><<<(unsigned)blocks, 256, smem, s>>>(in, V, Cin, Wt, bias, out_logits, out_argmax);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_linear_small_vec<CO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_linear_small_vec<CO, false><<<(unsigned)blocks, 256, smem, s>>>(in, V, Cin, Wt, bias, out_logits, out_argmax);
+    }
+}
+
 extern "C" int b2me_linear_small(const void* in, int in_dtype, int64_t V, int Cin, const float* Wt,
                                  const float* bias, int Cout, float* out_logits, uint8_t* out_argmax,
                                  b2me_stream_t stream) {
@@ -214,12 +315,23 @@ extern "C" int b2me_linear_small(const void* in, int in_dtype, int64_t V, int Ci
     const size_t smem = (size_t)Cout * Cin * sizeof(float);
     if (smem > 200 * 1024) return B2ME_EUNSUPPORTED;
     if (V == 0) return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int vec = in_dtype == B2ME_BF16 ? 8 : 4;
+    if (Cin % vec == 0 && Cin >= 32 * vec) {
+        switch (Cout) {
+#define LS_CASE(N) case N: launch_linear_small_vec<N>(in, in_dtype, V, Cin, Wt, bias, out_logits, out_argmax, smem, s); break;
+            LS_CASE(1) LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
+            LS_CASE(9) LS_CASE(10) LS_CASE(11) LS_CASE(12) LS_CASE(13) LS_CASE(14) LS_CASE(15) LS_CASE(16)
+#undef LS_CASE
+        }
+        B2ME_CHECK_LAUNCH();
+        return B2ME_OK;
+    }
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_linear_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = ceil_div64(V, 8);
     if (blocks > B2ME_NUM_SMS * 8) blocks = B2ME_NUM_SMS * 8;
-    k_linear_small<<<(unsigned)blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        in, in_dtype, V, Cin, Wt, bias, Cout, out_logits, out_argmax);
+    k_linear_small<<<(unsigned)blocks, 256, smem, s>>>(in, in_dtype, V, Cin, Wt, bias, Cout, out_logits, out_argmax);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

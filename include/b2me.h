@@ -148,9 +148,15 @@ int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, vo
                          b2me_stream_t stream);
 /* perm [V_out] i32 (may be null = identity): tile t computes the output rows perm[128 t .. 128 t + 127]; any
  * permutation gives bit-identical results (absent neighbours contribute exact zeros), a mask-sorted one
- * (b2me_mask_sort_keys) lets tiles skip the kernel offsets none of their rows has. */
+ * (b2me_mask_sort_keys64) lets tiles skip the kernel offsets none of their rows has.
+ * tile_masks [ceil(V_out / 256)] u32 (required when nbr is given): bit k set when any of the rows
+ * perm[256 t .. 256 t + 255] has neighbour k; computed once per (nbr, perm) by b2me_tc_tile_masks and shared by
+ * every convolution on that kernel map. */
+int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, int K, uint32_t* masks,
+                       b2me_stream_t stream);
 int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2,
-                       const void* packed_w, const int32_t* nbr, const int32_t* perm, int K,
+                       const void* packed_w, const int32_t* nbr, const int32_t* perm,
+                       const uint32_t* tile_masks, int K,
                        int64_t V_out, int Cout, const float* scale, const float* shift,
                        const void* residual, int act, float slope,
                        void* out, int out_dtype, b2me_stream_t stream);

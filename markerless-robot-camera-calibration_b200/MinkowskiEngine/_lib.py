@@ -7,7 +7,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2me.so")
+# B2ME_LIB_PATH: developer override used by tools/conv_probe.py to load an instrumented build (lib_debug/)
+LIB_PATH = os.environ.get("B2ME_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libb2me.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
@@ -33,8 +34,9 @@ SIGNATURES = {
     "b2me_tc_packed_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "b2me_tc_supported": (_i32, [_i32, _i32, _i32, _i32]),
     "b2me_tc_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32,
-                                  _vp, _i32, _vp]),
+    "b2me_tc_tile_masks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
+                                  _f32, _vp, _i32, _vp]),
     "b2me_affine_act": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "b2me_convert": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "b2me_linear_small": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),

@@ -90,6 +90,14 @@ def mask_sorted_perm(nbr, V, K, block_rows=None):
     return torch.sort(keys[:V])[1].to(torch.int32)
 
 
+def tile_masks(nbr, perm, V, K):
+    """per 256-row tile pair: the kernel offsets any of its rows needs (consumed by b2me_spconv_fwd_tc)."""
+    masks = torch.empty(((max(V, 1) + 255) // 256,), dtype=torch.int32, device=nbr.device)
+    check(lib.b2me_tc_tile_masks(ptr(nbr), ptr(perm), V, K, ptr(masks), stream()), "tc_tile_masks")
+    _count(1)
+    return masks
+
+
 def set_profile(mode):
     """None | 'census' | 'events' -> the record list that ops._profile_conv appends to."""
     _State.profile = None if mode is None else dict(mode=mode, records=[])
@@ -195,17 +203,21 @@ class CoordinateManager:
         return lv.nbr_k3
 
     def perm_k3(self, key):
+        """(row order, tile masks) of the k3 kernel map for the tcgen05 convolution."""
         lv = self.levels[key]
         if lv.perm_k3 is None:
-            lv.perm_k3 = mask_sorted_perm(self.kernel_map_k3(key), lv.V, 27)
+            nbr = self.kernel_map_k3(key)
+            perm = mask_sorted_perm(nbr, lv.V, 27) if _State.mask_sort else None
+            lv.perm_k3 = (perm, tile_masks(nbr, perm, lv.V, 27))
         return lv.perm_k3
 
     def perm_stride(self, rec, which):
-        """mask-sorted row order of the k2 s2 ("down") / transposed ("up") kernel map of a stride record."""
+        """(row order, tile masks) of the k2 s2 ("down") / transposed ("up") kernel map of a stride record."""
         name = "perm_" + which
         if rec.get(name) is None:
             nbr = rec["nbr_" + which]
-            rec[name] = mask_sorted_perm(nbr, nbr.shape[0], 8)
+            perm = mask_sorted_perm(nbr, nbr.shape[0], 8) if _State.mask_sort else None
+            rec[name] = (perm, tile_masks(nbr, perm, nbr.shape[0], 8))
         return rec[name]
 
     # -- K2
@@ -271,7 +283,7 @@ class _Pending:
     src: List["SparseTensor"]      # 1 or 2 sources (2 = lazy cat)
     module: object = None          # owner of the weights (conv / linear)
     nbr: Optional[torch.Tensor] = None
-    perm: object = None            # callable returning the mask-sorted row order of `nbr` (built on first use)
+    perm: object = None            # callable returning (row order, tile masks) of `nbr` (built on first use)
     K: int = 1
     V_out: int = 0
     Cout: int = 0

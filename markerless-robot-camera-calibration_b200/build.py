@@ -31,6 +31,12 @@ def _digest():
 
 
 def build(force=False, verbose=False):
+    global LIBDIR, LIB
+    extra = os.environ.get("B2ME_EXTRA_NVCC_FLAGS", "").split()
+    if extra:  # debug variants (e.g. -DB2ME_TC_PROFILE) are built beside the product library, never over it
+        LIBDIR = os.path.join(HERE, "lib_debug")
+        LIB = os.path.join(LIBDIR, "libb2me.so")
+        NVCC_FLAGS.extend(extra)
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "libb2me.digest")
     dig = _digest()

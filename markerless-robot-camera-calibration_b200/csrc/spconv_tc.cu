@@ -1,21 +1,28 @@
 // spconv_tc.cu — K4b: sparse convolution as an output-stationary implicit GEMM on tcgen05 (sm_100a).
 //
-// PERSISTENT, warp-specialised kernel: one CTA per SM walks the work list (128-row tile x n-tile) round-robin.
+// PERSISTENT, warp-specialised kernel on CTA PAIRS (cta_group::2): a cluster of two CTAs (one TPC) walks the work
+// list (256-row tile pair x n-tile) round-robin; each CTA gathers the A rows of its own 128-row tile and loads HALF
+// of every weight tile, the leader CTA issues M = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM
+// holds the accumulator of its own 128 rows. Halving the per-SM weight traffic is what lets the stage ring be deep
+// enough (5 x 40 KB at n_tile = 384) to cover the DRAM latency of the gathered rows.
 //
-//   work item     128 output voxels (rows perm[128 t ..]) x n_tile output channels (n_tile <= 384 TMEM columns)
+//   work item     2 x 128 output voxels (rows perm[256 t ..]) x n_tile output channels (n_tile <= 384 TMEM columns)
 //   reduction     items = (kernel offset k with at least one neighbour in the tile) x (64-channel chunk)
 //   A operand     128 gathered input rows x 64 bf16 (= one 128-byte swizzle row per voxel), cp.async 16-byte
 //                 pieces straight into the SWIZZLE_128B K-major smem image, zero-fill for missing neighbours
-//   B operand     W[k][chunk] pre-packed on the host side of the ABI into the exact smem image, so one
-//                 cp.async.bulk (UBLKCP) per item brings n_tile x 128 bytes and completes on the stage mbarrier
-//   MMA           one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16), fp32
-//                 accumulators stay in TMEM for the whole tile
+//   B operand     W[k][chunk] pre-packed on the host side of the ABI into the exact smem image of each CTA's half,
+//                 so one cp.async.bulk (UBLKCP) per item brings n_tile/2 x 128 bytes and completes on the stage
+//                 mbarrier
+//   MMA           one elected thread of the leader CTA issues tcgen05.mma.cta_group::2.kind::f16 (M=256, N<=256,
+//                 K=16), fp32 accumulators stay in TMEM for the whole tile; tcgen05.commit multicasts the stage
+//                 release / accumulator-ready arrivals to both CTAs
 //   epilogue      tcgen05.ld -> folded BatchNorm scale/shift, residual add, ReLU/LeakyReLU -> bf16 rows, staged
 //                 through shared memory so that residual loads and output stores are 64-byte coalesced segments
 //
 //   warps  0-3    gather producers (stage ring runs on across tiles, so the next tile's rows are in flight while
 //                 the tensor pipe finishes the current one)
-//          4      TMEM alloc + MMA issuer            5      weight (B) bulk-copy issuer
+//          4      TMEM alloc + MMA issuer (leader) / stage-full relay to the leader's barrier (peer)
+//          5      weight (B) bulk-copy issuer
 //          6-7    kernel-map prefetch: the NEXT tile's 128 x K neighbour rows go global -> registers while the
 //                 current tile runs, then registers -> smem the moment the producers release the buffer
 //          8-11   epilogue (warp w owns TMEM lanes 32 (w-8) ..); overlaps the next tile's gathers
@@ -30,7 +37,9 @@
 #define TC_BM 128
 #define TC_BK 64
 #define TC_A_BYTES (TC_BM * 128)
-#define TC_THREADS 384
+#define TC_THREADS 512
+#define TC_EPI_WARPS 8
+#define TC_NSPLIT0 256  // N of the first MMA of a K step when the tile is wider than 256 columns
 #define TC_MAX_STAGES 8
 #define TC_MAX_SMEM 232448
 #define TC_MIN_SMEM (120 * 1024)  // more than half an SM: one CTA per SM, so a 512-column TMEM alloc never blocks
@@ -42,6 +51,7 @@ struct TcParams {
     const uint8_t* wpacked;
     const int32_t* nbr;
     const int32_t* perm;
+    const uint32_t* tile_masks;
     const float* scale;
     const float* shift;
     const __nv_bfloat16* residual;
@@ -52,8 +62,32 @@ struct TcParams {
     int act, out_dtype, tmem_cols;
     float slope;
     unsigned int b_bytes;
-    int total_work;  // row tiles x n-tiles
+    int total_work;  // 256-row tile pairs x n-tiles
 };
+
+// Optional in-kernel role timers (build with -DB2ME_TC_PROFILE; tools/conv_probe.py): cycles that lane 0 of each
+// role of cluster 0 spends in each wait, accumulated over launches. Not compiled into the product library.
+#ifdef B2ME_TC_PROFILE
+__device__ unsigned long long g_tc_prof[2][8][8];  // [cta rank][role][counter]
+#define PROF_DECL unsigned long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_ = 0; (void)pt_;
+#define PROF(slot, stmt) do { pt_ = clock64(); stmt; prof_[slot] += (unsigned long long)(clock64() - pt_); } while (0)
+#define PROF_COUNT(slot) (++prof_[slot])
+#define PROF_DUMP(role) do { if (blockIdx.x < 2 && lane == 0) for (int q_ = 0; q_ < 8; ++q_) \
+        atomicAdd(&g_tc_prof[rank][role][q_], prof_[q_]); } while (0)
+extern "C" int b2me_tc_prof_read(unsigned long long* host_out, int reset) {
+    if (host_out && cudaMemcpyFromSymbol(host_out, g_tc_prof, sizeof(g_tc_prof)) != cudaSuccess) return B2ME_ELAUNCH;
+    if (reset) {
+        static unsigned long long zero[2 * 8 * 8];
+        if (cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)) != cudaSuccess) return B2ME_ELAUNCH;
+    }
+    return B2ME_OK;
+}
+#else
+#define PROF_DECL
+#define PROF(slot, stmt) stmt
+#define PROF_COUNT(slot)
+#define PROF_DUMP(role)
+#endif
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +178,54 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+// wait whose acquire covers arrivals made by the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
@@ -156,9 +238,12 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// N of the MMA instructions of one item: n_tile <= 256 -> one instruction; wider tiles -> TC_NSPLIT0 + the rest.
+__host__ __device__ __forceinline__ int tc_n_first(int n_tile) { return n_tile > 256 ? TC_NSPLIT0 : n_tile; }
+
 // KT = kernel volume of the map (27: k3 s1, 8: k2 s2 and its transpose, 1: identity / MinkowskiLinear)
 template <int KT>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -168,67 +253,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
     const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
-    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 4 x 2 KB][barriers][kmask][tmem ptr]
+    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 8 x 2 KB][barriers][tmem ptr]
     uint32_t off = (uint32_t)S * stage_bytes;
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
     off += TC_BM * KT * 4;
+    off = (off + 15u) & ~15u;
     float* scale_s = reinterpret_cast<float*>(sm + off);
     off += p.Cout * 4;
     float* shift_s = reinterpret_cast<float*>(sm + off);
     off += p.Cout * 4;
     off = (off + 15u) & ~15u;
     const uint32_t stage_out = base + off;
-    off += 4 * TC_STAGE_OUT_BYTES;
+    off += TC_EPI_WARPS * TC_STAGE_OUT_BYTES;
     const uint32_t bar_full = base + off;
     off += 8 * TC_MAX_STAGES;
     const uint32_t bar_empty = base + off;
     off += 8 * TC_MAX_STAGES;
-    const uint32_t bar_nbr_full = base + off;  // [2]
-    off += 16;
+    const uint32_t bar_nbr_full = base + off;
+    off += 8;
     const uint32_t bar_nbr_empty = base + off;
     off += 8;
-    const uint32_t bar_kmask_empty = base + off;  // [2]
-    off += 16;
     const uint32_t bar_tmem_full = base + off;
     off += 8;
     const uint32_t bar_tmem_empty = base + off;
     off += 8;
-    volatile uint32_t* kmask_s = reinterpret_cast<volatile uint32_t*>(sm + off);  // [2 buffers][2 prefetch warps]
-    off += 16;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + off);
 
     // ---- one-time setup
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(bar_full + 8 * s, 129); // 128 producer threads (cp.async-completion arrivals) + the B expect_tx arrive
-            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
+            // 128 producer threads (cp.async-completion arrivals) + the B expect_tx arrive (+ the peer's relay)
+            mbar_init(bar_full + 8 * s, rank == 0 ? 130 : 129);
+            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit (multicast from the leader)
         }
-        mbar_init(bar_nbr_full, 2);
-        mbar_init(bar_nbr_full + 8, 2);
-        mbar_init(bar_nbr_empty, 4);
-        mbar_init(bar_kmask_empty, 2);
-        mbar_init(bar_kmask_empty + 8, 2);
-        mbar_init(bar_tmem_full, 1);
-        mbar_init(bar_tmem_empty, 4);
+        mbar_init(bar_nbr_full, 2);            // 2 prefetch warps
+        mbar_init(bar_nbr_empty, 4);           // 4 producer warps
+        mbar_init(bar_tmem_full, 1);           // tcgen05.commit (multicast from the leader)
+        mbar_init(bar_tmem_empty, 2 * TC_EPI_WARPS);  // epilogue warps of both CTAs (leader's barrier only)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+        // cta_group::2 allocation: the same warp of both CTAs issues it
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
                      "r"((uint32_t)p.tmem_cols)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < p.Cout; i += TC_THREADS) {
         scale_s[i] = p.scale ? p.scale[i] : 1.f;
         shift_s[i] = p.shift ? p.shift[i] : 0.f;
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     const int nchunk = p.nchunk1 + p.nchunk2;
-    const int G = gridDim.x;
+    const int G = gridDim.x >> 1;          // clusters
+    const int unit0 = blockIdx.x >> 1;     // this cluster's first work item
+    // offsets (bit k) that at least one row of a 256-row tile pair needs: precomputed per map (b2me_tc_tile_masks),
+    // so every role knows a tile's item list without waiting for the kernel-map rows
+    auto tile_mask = [&](int w) -> uint32_t {
+        if (!p.tile_masks) return 1u;
+        const uint32_t m = __ldg(p.tile_masks + w / p.n_ntiles);
+        return m ? m : 1u;
+    };
 
     if (warp < 4) {
         // =============================== gather producers ===============================
@@ -236,11 +326,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
         const int rbase = tid >> 3;   // rows rbase + 16*i
         int ist = 0, iph = 0;         // stage / phase of the next item to issue
         int it = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
-            const int b = it & 1;
-            mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
-            uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
-            if (!kmask) kmask = 1u;
+        PROF_DECL
+        const long long t_role0 = clock64();
+        (void)t_role0;
+        uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+        for (int w = unit0; w < p.total_work; w += G, ++it) {
+            const uint32_t kmask = kmask_next;
+            if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+            PROF(1, mbar_wait(bar_nbr_full, (uint32_t)it & 1u));
 #pragma unroll 1
             for (int k = 0; k < KT; ++k) {
                 if (!((kmask >> k) & 1u)) continue;
@@ -253,7 +346,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
-                    mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u);
+                    PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
+                    PROF_COUNT(7);
                     const __nv_bfloat16* src;
                     int cin, coff;
                     if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
@@ -277,20 +371,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                 }
             }
         }
+#ifdef B2ME_TC_PROFILE
+        prof_[0] = (unsigned long long)(clock64() - t_role0);
+        if (warp == 0) PROF_DUMP(0);
+#endif
     } else if (warp == 4) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const int nhalf = p.n_tile > 256 ? 2 : 1;
-            const int nh = p.n_tile / nhalf;
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nh >> 3) << 17) | (8u << 24);
+        // =============================== MMA issuer (leader) / stage relay (peer) ===============================
+        if (lane == 0 && rank == 0) {
+            const int n_a = tc_n_first(p.n_tile), n_b = p.n_tile - n_a;  // N of the one or two MMAs per K step
+            // kind::f16, bf16 x bf16 -> f32, K-major A and B, M = 256 (cta_group::2); each CTA's smem holds N/2 rows
+            const uint32_t idesc_a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_a >> 3) << 17) | (16u << 24);
+            const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_b >> 3) << 17) | (16u << 24);
             int st = 0, ph = 0, it = 0;
-            for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
-                const int b = it & 1;
-                mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
-                uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
-                if (!kmask) kmask = 1u;
-                if (it > 0) {  // the epilogue of the previous tile must have drained the accumulator
-                    mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u);
+            PROF_DECL
+            const long long t_role0 = clock64();
+            (void)t_role0;
+            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+            for (int w = unit0; w < p.total_work; w += G, ++it) {
+                const uint32_t kmask = kmask_next;
+                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+                if (it > 0) {  // both CTAs' epilogues of the previous tile pair must have drained their accumulators
+                    PROF(2, mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u));
                     tc_fence_after();
                 }
                 uint32_t acc = 0u;
@@ -299,50 +400,86 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                     for (int c = 0; c < nchunk; ++c) {
                         const int kw = (c < p.nchunk1) ? min(TC_BK, p.Cin1 - c * TC_BK)
                                                        : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
-                        mbar_wait(bar_full + 8 * st, (uint32_t)ph);
-                        fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA's async proxy
+                        PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
+                        PROF_COUNT(7);
+                        fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
                         tc_fence_after();
+#ifdef B2ME_TC_PROFILE
+                        pt_ = clock64();
+#endif
                         const uint32_t a_s = base + (uint32_t)st * stage_bytes;
                         const uint32_t b_s = a_s + TC_A_BYTES;
                         const uint64_t adesc = make_smem_desc_sw128(a_s);
+                        const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
+                        const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
                         for (int kk = 0; kk < kw / 16; ++kk) {
-                            for (int h = 0; h < nhalf; ++h) {
-                                const uint64_t bdesc = make_smem_desc_sw128(b_s + (uint32_t)(h * nh) * 128u);
-                                tc_mma_bf16(tmem_base + (uint32_t)(h * nh), adesc + (uint64_t)(kk * 2),
-                                            bdesc + (uint64_t)(kk * 2), idesc, acc);
-                            }
+                            tc_mma_bf16_pair(tmem_base, adesc + (uint64_t)(kk * 2), bdesc_a + (uint64_t)(kk * 2), idesc_a,
+                                             acc);
+                            if (n_b)
+                                tc_mma_bf16_pair(tmem_base + (uint32_t)n_a, adesc + (uint64_t)(kk * 2),
+                                                 bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
                             acc = 1u;
                         }
-                        tc_commit(bar_empty + 8 * st);
+                        tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
+#ifdef B2ME_TC_PROFILE
+                        prof_[5] += (unsigned long long)(clock64() - pt_);
+#endif
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
-                tc_commit(bar_tmem_full);
-                mbar_arrive(bar_kmask_empty + 8 * b);
+                tc_commit_pair(bar_tmem_full);  // accumulators of both CTAs are complete
             }
+#ifdef B2ME_TC_PROFILE
+            prof_[0] = (unsigned long long)(clock64() - t_role0);
+            PROF_DUMP(1);
+#endif
+        } else if (lane == 0) {
+            // peer: when a stage of THIS CTA is full (A gathered, B landed), tell the leader's full barrier
+            int st = 0, ph = 0;
+            PROF_DECL
+            const long long t_role0 = clock64();
+            (void)t_role0;
+            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+            for (int w = unit0; w < p.total_work; w += G) {
+                const uint32_t kmask = kmask_next;
+                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+                for (int k = 0; k < KT; ++k) {
+                    if (!((kmask >> k) & 1u)) continue;
+                    for (int c = 0; c < nchunk; ++c) {
+                        PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
+                        PROF_COUNT(7);
+                        PROF(4, fence_proxy_async());
+                        PROF(5, mbar_arrive_remote(bar_full + 8 * st, 0u));
+                        if (++st == S) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+#ifdef B2ME_TC_PROFILE
+            prof_[0] = (unsigned long long)(clock64() - t_role0);
+            PROF_DUMP(5);
+#endif
         }
     } else if (warp == 5) {
         // =============================== weight (B) loader ===============================
         if (lane == 0) {
-            int st = 0, ph = 0, it = 0;
-            for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
-                const int b = it & 1;
+            int st = 0, ph = 0;
+            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+            for (int w = unit0; w < p.total_work; w += G) {
+                const uint32_t kmask = kmask_next;
+                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
                 const int nt = w % p.n_ntiles;
-                mbar_wait(bar_nbr_full + 8 * b, (uint32_t)(it >> 1) & 1u);
-                uint32_t kmask = kmask_s[2 * b] | kmask_s[2 * b + 1];
-                if (!kmask) kmask = 1u;
                 for (int k = 0; k < KT; ++k) {
                     if (!((kmask >> k) & 1u)) continue;
                     for (int c = 0; c < nchunk; ++c) {
                         mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
                         const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
-                        const uint8_t* g = p.wpacked + ((size_t)((size_t)nt * KT + k) * nchunk + c) * (size_t)p.b_bytes;
+                        const uint8_t* g =
+                            p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
                         mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
                         bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
-                mbar_arrive(bar_kmask_empty + 8 * b);
             }
         }
     } else if (warp < 8) {
@@ -352,9 +489,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
         const int wl = warp - 6;
         constexpr int NJ = 2 * KT;
         int it = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
-            const int b = it & 1;
-            const long long row0 = (long long)(w / p.n_ntiles) * TC_BM + 64 * wl;
+        for (int w = unit0; w < p.total_work; w += G, ++it) {
+            const long long row0 = ((long long)(w / p.n_ntiles) * 2 + rank) * TC_BM + 64 * wl;
             int rowreg[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -362,7 +498,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                 rowreg[h] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
             }
             int v[NJ];
-            uint32_t local = 0u;
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
                 const int e = lane + 32 * jj;  // < 64 * KT
@@ -370,36 +505,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                 const int r0 = __shfl_sync(0xffffffffu, rowreg[0], rl & 31);
                 const int r1 = __shfl_sync(0xffffffffu, rowreg[1], rl & 31);
                 const int row = (rl >> 5) ? r1 : r0;
-                int val;
-                if (p.nbr) val = (row >= 0) ? __ldg(p.nbr + (long long)row * KT + k) : -1;
-                else val = row;
-                v[jj] = val;
-                if (val >= 0) local |= 1u << k;
+                if (p.nbr) v[jj] = (row >= 0) ? __ldg(p.nbr + (long long)row * KT + k) : -1;
+                else v[jj] = row;
             }
-            local = __reduce_or_sync(0xffffffffu, local);
             if (it >= 1) mbar_wait(bar_nbr_empty, (uint32_t)(it - 1) & 1u);
-            if (it >= 2) mbar_wait(bar_kmask_empty + 8 * b, (uint32_t)((it >> 1) - 1) & 1u);
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) nbr_s[64 * wl * KT + lane + 32 * jj] = v[jj];
-            if (lane == 0) kmask_s[2 * b + wl] = local;
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_nbr_full + 8 * b);
+            if (lane == 0) mbar_arrive(bar_nbr_full);
         }
     } else {
         // =============================== epilogue ===============================
-        const int we = warp - 8;  // TMEM lanes 32 we .. 32 we + 31  (warp % 4 == we)
+        // 8 warps: warp e handles TMEM lanes 32 (e & 3) .. (a warp may only touch the lane quarter warp_id % 4) and
+        // the column half e >> 2 of the tile
+        const int ew = warp - 8;
+        const int we = ew & 3, chalf = ew >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(we * 32) << 16);
-        const uint32_t stg = stage_out + (uint32_t)we * TC_STAGE_OUT_BYTES;
+        const uint32_t stg = stage_out + (uint32_t)ew * TC_STAGE_OUT_BYTES;
         // staging image: row r (0..31) = 64 bytes, 16-byte piece q stored at q ^ ((r >> 1) & 3): conflict-free for both
         // the row-per-lane view (lane = row) and the coalesced view (4 lanes per row, 8 rows per access)
         const uint32_t own = stg + (uint32_t)lane * 64u;
         const int own_sw = (lane >> 1) & 3;
         const int crow = lane >> 2, cq = lane & 3;  // coalesced view: rows crow + 8 m, piece cq
+        // this warp's columns: 32-column chunks [c_lo, c_hi) of the tile
+        const int nch = (p.n_tile + 31) >> 5;
+        const int c_lo = chalf ? ((nch + 1) >> 1) * 32 : 0;
+        const int c_hi = chalf ? p.n_tile : min(p.n_tile, ((nch + 1) >> 1) * 32);
         int it = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += G, ++it) {
-            const int tile_m = w / p.n_ntiles;
-            const int n0 = (w - tile_m * p.n_ntiles) * p.n_tile;
-            const long long slot = (long long)tile_m * TC_BM + we * 32 + lane;
+        PROF_DECL
+        for (int w = unit0; w < p.total_work; w += G, ++it) {
+            const int tile_p = w / p.n_ntiles;
+            const int n0 = (w - tile_p * p.n_ntiles) * p.n_tile;
+            const long long slot = ((long long)tile_p * 2 + rank) * TC_BM + we * 32 + lane;
             const int row = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
             int crows[4];  // output rows of the coalesced view
 #pragma unroll
@@ -419,10 +556,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                                                                         cq * 8));
                     }
                 };
-                if (resp) load_res(0);
-                mbar_wait(bar_tmem_full, (uint32_t)it & 1u);
+                if (resp && c_lo < c_hi) load_res(c_lo);
+                PROF(1, mbar_wait(bar_tmem_full, (uint32_t)it & 1u));
                 tc_fence_after();
-                for (int cb = 0; cb < p.n_tile; cb += 32) {
+#ifdef B2ME_TC_PROFILE
+                const long long t_epi0 = clock64();
+#endif
+                if (c_lo >= c_hi) {  // narrow tile: this warp has no columns
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
+                }
+                for (int cb = c_lo; cb < c_hi; cb += 32) {
                     const int cw = min(32, p.n_tile - cb);
                     uint32_t r[32];
                     if (cw == 32) {
@@ -439,19 +583,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                             st_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4), R[m]);
                         }
                         __syncwarp();
-                        if (cb + 32 < p.n_tile) load_res(cb + 32);  // in flight during this chunk's math and stores
+                        if (cb + 32 < c_hi) load_res(cb + 32);  // in flight during this chunk's math and stores
                     }
                     tmem_ld_wait();
-                    if (cb + 32 >= p.n_tile) {  // accumulator fully read: the next tile's MMAs may start
+                    if (cb + 32 >= c_hi) {  // this warp's part of the accumulator is read: release it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tmem_empty);
+                        if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);  // the leader's barrier
                     }
                     float v[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int col = min(n0 + cb + q, p.Cout - 1);
-                        v[q] = __uint_as_float(r[q]) * scale_s[col] + shift_s[col];
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
+                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
+                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                        v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                        v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                        v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                        v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
                     }
                     if (resp) {
 #pragma unroll
@@ -488,18 +637,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                     }
                     __syncwarp();  // staging is reused by the next chunk
                 }
+#ifdef B2ME_TC_PROFILE
+                prof_[2] += (unsigned long long)(clock64() - t_epi0);
+                ++prof_[7];
+#endif
             } else {
-                // fp32 rows (parity tests only): row-per-lane stores
+                // fp32 rows (parity tests only): row-per-lane stores, 16-column chunks split between the two halves
                 mbar_wait(bar_tmem_full, (uint32_t)it & 1u);
                 tc_fence_after();
-                for (int cb = 0; cb < p.n_tile; cb += 16) {
+                const int n16 = p.n_tile >> 4;
+                const int q_lo = chalf ? (n16 + 1) >> 1 : 0, q_hi = chalf ? n16 : (n16 + 1) >> 1;
+                if (q_lo >= q_hi) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
+                }
+                for (int qc = q_lo; qc < q_hi; ++qc) {
+                    const int cb = qc * 16;
                     uint32_t r[16];
                     tmem_ld_x16(lane_addr + (uint32_t)cb, r);
                     tmem_ld_wait();
-                    if (cb + 16 >= p.n_tile) {
+                    if (qc + 1 >= q_hi) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tmem_empty);
+                        if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
                     }
                     if (row < 0) continue;
                     float v[16];
@@ -526,14 +686,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
                 }
             }
         }
+#ifdef B2ME_TC_PROFILE
+        if (warp == 8) PROF_DUMP(4);
+#endif
     }
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
     if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)p.tmem_cols)
                      : "memory");
     }
+}
+
+// one warp per 256-row tile pair: OR of the neighbour-occupancy masks of its rows
+__global__ void __launch_bounds__(256) k_tc_tile_masks(const int32_t* __restrict__ nbr, const int32_t* __restrict__ perm,
+                                                       long long V, int K, uint32_t* __restrict__ masks,
+                                                       long long npairs) {
+    const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= npairs) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t m = 0u;
+    for (int r = 0; r < 2 * TC_BM; ++r) {
+        const long long slot = pair * (2 * TC_BM) + r;
+        if (slot >= V) break;
+        const long long row = perm ? __ldg(perm + slot) : slot;
+        if (lane < K && __ldg(nbr + row * K + lane) >= 0) m |= 1u << lane;
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0) masks[pair] = m;
+}
+
+extern "C" int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, int K, uint32_t* masks,
+                                  b2me_stream_t stream) {
+    if (!nbr || !masks || V_out < 0 || K < 1 || K > 32) return B2ME_EINVAL;
+    if (V_out == 0) return B2ME_OK;
+    const long long npairs = ceil_div64(V_out, 2 * TC_BM);
+    k_tc_tile_masks<<<(unsigned)ceil_div64(npairs, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        nbr, perm, V_out, K, masks, npairs);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -547,7 +740,7 @@ extern "C" int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout) {
     if (Cin1 % 16 || Cin2 % 16 || Cout % 16) return 0;
     const int nt = tc_n_tile(Cout);
     if (Cout % nt) return 0;
-    if (nt > 256 && (nt % 32)) return 0;
+    if (nt > 256 && ((nt - TC_NSPLIT0) % 16 || nt - TC_NSPLIT0 < 32)) return 0;
     return 1;
 }
 
@@ -587,8 +780,17 @@ __global__ void k_tc_pack(const float* __restrict__ W, int K, int Cin1, int Cin2
         __nv_bfloat162 v = __floats2bfloat162_rn(f[0], f[1]);
         w[e] = *reinterpret_cast<uint32_t*>(&v);
     }
+    // image of one item = [cta rank 0 | cta rank 1]; a CTA's part = its half of the rows of each of the (one or two)
+    // MMA instructions of a K step: instruction a covers columns [0, n_a), instruction b covers [n_a, n_tile)
+    const int n_a = tc_n_first(n_tile);
+    const int in_b = n >= n_a;
+    const int nseg = in_b ? n_tile - n_a : n_a;       // N of the instruction this column belongs to
+    const int nn = in_b ? n - n_a : n;
+    const int q = nseg / 2;
+    const int r = nn / q;
+    const int lrow = (in_b ? n_a / 2 : 0) + (nn - r * q);
     const long long item = ((long long)nt * K + k) * nchunk + c;
-    const long long piece = item * ((long long)n_tile * 8) + (long long)n * 8 + (j ^ (n & 7));
+    const long long piece = (item * 2 + r) * ((long long)(n_tile / 2) * 8) + (long long)lrow * 8 + (j ^ (lrow & 7));
     packed[piece] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -627,19 +829,21 @@ static int tc_launch(const TcParams& p, size_t smem, cudaStream_t stream) {
             return B2ME_ELAUNCH;
         attr_set = true;
     }
-    const int grid = p.total_work < tc_num_sms() ? p.total_work : tc_num_sms();
-    k_spconv_tc<KT><<<grid, TC_THREADS, smem, stream>>>(p);
+    const int clusters = p.total_work < tc_num_sms() / 2 ? p.total_work : tc_num_sms() / 2;
+    k_spconv_tc<KT><<<2 * clusters, TC_THREADS, smem, stream>>>(p);  // __cluster_dims__(2,1,1): CTA pairs
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
 
 extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, const void* packed_w,
-                                  const int32_t* nbr, const int32_t* perm, int K, int64_t V_out, int Cout,
+                                  const int32_t* nbr, const int32_t* perm, const uint32_t* tile_masks, int K,
+                                  int64_t V_out, int Cout,
                                   const float* scale, const float* shift, const void* residual, int act, float slope,
                                   void* out, int out_dtype, b2me_stream_t stream) {
     if (!in1 || !packed_w || !out || V_out < 0) return B2ME_EINVAL;
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
+    if (nbr && !tile_masks) return B2ME_EINVAL;
     if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
     if (out_dtype != B2ME_BF16 && out_dtype != B2ME_F32) return B2ME_EINVAL;
     if (V_out == 0) return B2ME_OK;
@@ -650,6 +854,7 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.wpacked = reinterpret_cast<const uint8_t*>(packed_w);
     p.nbr = nbr;
     p.perm = perm;
+    p.tile_masks = nbr ? tile_masks : nullptr;
     p.scale = scale;
     p.shift = shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
@@ -665,16 +870,16 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.act = act;
     p.out_dtype = out_dtype;
     p.slope = slope;
-    p.b_bytes = (unsigned)p.n_tile * 128u;
+    p.b_bytes = (unsigned)(p.n_tile / 2) * 128u;  // each CTA of the pair stages half of every weight tile
     int cols = 32;
     while (cols < p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
-    const int64_t work = ceil_div64(V_out, TC_BM) * p.n_ntiles;
+    const int64_t work = ceil_div64(V_out, 2 * TC_BM) * p.n_ntiles;  // 256-row tile pairs x n-tiles
     if (work > 0x7fffffff) return B2ME_EUNSUPPORTED;
     p.total_work = (int)work;
 
-    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + (size_t)Cout * 8 + 16 +
-                         4 * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 16 + 8 + 16 + 8 + 8 + 16 + 16;
+    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 +
+                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 4 * 8 + 16;
     const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
     int S = TC_MAX_STAGES;
     while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;

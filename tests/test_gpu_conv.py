@@ -53,8 +53,11 @@ def _call_tc(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torch.
     packed = torch.empty((lib.b2me_tc_packed_bytes(K, c1, c2, Cout),), dtype=torch.uint8, device="cuda")
     check(lib.b2me_tc_pack_weights(ptr(W), K, c1, c2, Cout, ptr(packed), stream()))
     out = torch.empty((V_out, Cout), dtype=out_dtype, device="cuda")
-    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, ptr(packed), ptr(nbr), ptr(perm), K, V_out, Cout, ptr(scale),
-                                 ptr(shift), ptr(res), act, 0.01, ptr(out), dtype_code(out_dtype), stream()))
+    import MinkowskiEngine as ME
+    masks = ME.tile_masks(nbr, perm, V_out, K) if nbr is not None else None
+    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V_out, Cout,
+                                 ptr(scale), ptr(shift), ptr(res), act, 0.01, ptr(out), dtype_code(out_dtype),
+                                 stream()))
     torch.cuda.synchronize()
     return out
 

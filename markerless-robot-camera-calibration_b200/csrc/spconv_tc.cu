@@ -33,12 +33,16 @@
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define TC_BM 128
 #define TC_BK 64
 #define TC_A_BYTES (TC_BM * 128)
 #define TC_THREADS 512
 #define TC_EPI_WARPS 8
+#ifndef TC_L2_PREFETCH
+#define TC_L2_PREFETCH 1  // producers prefetch the next offset's rows into L2
+#endif
 #define TC_NSPLIT0 256  // N of the first MMA of a K step when the tile is wider than 256 columns
 #define TC_MAX_STAGES 8
 #define TC_MAX_SMEM 232448
@@ -125,6 +129,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
 // the executing thread's arrival on `bar` fires when all of its prior cp.async copies have landed (no wait_group)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -343,6 +350,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
+                } else if (TC_L2_PREFETCH && j < nchunk) {
+                    // the gathered rows come from all over the tensor (DRAM latency >> the ring's depth in time): pull
+                    // the rows of the NEXT offset into L2 now, one whole offset (= nchunk items) ahead of their gather.
+                    // lane j takes the 128-byte chunk j of each of this thread's 8 rows.
+                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
+                    const __nv_bfloat16* psrc;
+                    int pcin, pcoff;
+                    if (j < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = j * TC_BK; }
+                    else { psrc = p.in2; pcin = p.Cin2; pcoff = (j - p.nchunk1) * TC_BK; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int id = nbr_s[(rbase + 16 * i) * KT + k2];
+                        if (id >= 0) prefetch_l2(psrc + (long long)id * pcin + pcoff);
+                    }
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
@@ -884,6 +905,12 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     int S = TC_MAX_STAGES;
     while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
     if (S < 3) return B2ME_EUNSUPPORTED;
+#ifdef B2ME_TC_PROFILE
+    if (const char* e = getenv("B2ME_TC_STAGES")) {  // debug build only: ring-depth experiments
+        const int want = atoi(e);
+        if (want >= 2 && want < S) S = want;
+    }
+#endif
     p.stages = S;
     size_t smem = fixed + (size_t)S * stage_bytes;
     if (smem < TC_MIN_SMEM) smem = TC_MIN_SMEM;

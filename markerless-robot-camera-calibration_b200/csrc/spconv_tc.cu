@@ -398,7 +398,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
 #endif
     } else if (warp == 4) {
         // =============================== MMA issuer (leader) / stage relay (peer) ===============================
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the item list and waits on the barriers; lane 0 alone issues the tcgen05 instructions
+        // (measured: a wait executed by a lone lane of a divergent warp costs ~210 cycles even on a complete phase).
+        if (rank == 0) {
             const int n_a = tc_n_first(p.n_tile), n_b = p.n_tile - n_a;  // N of the one or two MMAs per K step
             // kind::f16, bf16 x bf16 -> f32, K-major A and B, M = 256 (cta_group::2); each CTA's smem holds N/2 rows
             const uint32_t idesc_a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_a >> 3) << 17) | (16u << 24);
@@ -423,38 +425,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                                                        : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
                         PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
                         PROF_COUNT(7);
-                        fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
-                        tc_fence_after();
 #ifdef B2ME_TC_PROFILE
                         pt_ = clock64();
 #endif
-                        const uint32_t a_s = base + (uint32_t)st * stage_bytes;
-                        const uint32_t b_s = a_s + TC_A_BYTES;
-                        const uint64_t adesc = make_smem_desc_sw128(a_s);
-                        const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
-                        const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
-                        for (int kk = 0; kk < kw / 16; ++kk) {
-                            tc_mma_bf16_pair(tmem_base, adesc + (uint64_t)(kk * 2), bdesc_a + (uint64_t)(kk * 2), idesc_a,
-                                             acc);
-                            if (n_b)
-                                tc_mma_bf16_pair(tmem_base + (uint32_t)n_a, adesc + (uint64_t)(kk * 2),
-                                                 bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
-                            acc = 1u;
+                        if (lane == 0) {
+                            fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
+                            tc_fence_after();
+                            const uint32_t a_s = base + (uint32_t)st * stage_bytes;
+                            const uint32_t b_s = a_s + TC_A_BYTES;
+                            const uint64_t adesc = make_smem_desc_sw128(a_s);
+                            const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
+                            const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
+                            for (int kk = 0; kk < kw / 16; ++kk) {
+                                tc_mma_bf16_pair(tmem_base, adesc + (uint64_t)(kk * 2), bdesc_a + (uint64_t)(kk * 2),
+                                                 idesc_a, acc);
+                                if (n_b)
+                                    tc_mma_bf16_pair(tmem_base + (uint32_t)n_a, adesc + (uint64_t)(kk * 2),
+                                                     bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
+                                acc = 1u;
+                            }
+                            tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
                         }
-                        tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
+                        __syncwarp();
 #ifdef B2ME_TC_PROFILE
                         prof_[5] += (unsigned long long)(clock64() - pt_);
 #endif
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
-                tc_commit_pair(bar_tmem_full);  // accumulators of both CTAs are complete
+                if (lane == 0) tc_commit_pair(bar_tmem_full);  // accumulators of both CTAs are complete
+                __syncwarp();
             }
 #ifdef B2ME_TC_PROFILE
             prof_[0] = (unsigned long long)(clock64() - t_role0);
             PROF_DUMP(1);
 #endif
-        } else if (lane == 0) {
+        } else {
             // peer: when a stage of THIS CTA is full (A gathered, B landed), tell the leader's full barrier
             int st = 0, ph = 0;
             PROF_DECL
@@ -469,8 +475,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     for (int c = 0; c < nchunk; ++c) {
                         PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
                         PROF_COUNT(7);
-                        PROF(4, fence_proxy_async());
-                        PROF(5, mbar_arrive_remote(bar_full + 8 * st, 0u));
+                        if (lane == 0) {
+                            fence_proxy_async();
+                            mbar_arrive_remote(bar_full + 8 * st, 0u);
+                        }
+                        __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
@@ -482,7 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         }
     } else if (warp == 5) {
         // =============================== weight (B) loader ===============================
-        if (lane == 0) {
+        {
             int st = 0, ph = 0;
             uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
             for (int w = unit0; w < p.total_work; w += G) {
@@ -493,11 +502,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     if (!((kmask >> k) & 1u)) continue;
                     for (int c = 0; c < nchunk; ++c) {
                         mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
-                        const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
-                        const uint8_t* g =
-                            p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
-                        mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
-                        bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
+                        if (lane == 0) {
+                            const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
+                            const uint8_t* g =
+                                p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
+                            mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
+                            bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
+                        }
+                        __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }

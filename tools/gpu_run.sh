@@ -1,9 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-export B2ME_LIB_PATH=$GRAFT_REPO_ROOT/markerless-robot-camera-calibration_b200/lib_debug/libb2me.so
-for st in 2 3 4; do
-B2ME_TC_STAGES=$st timeout 300 python tools/conv_probe.py --frames 8 --shapes 27:384:384 > gpurun_out/probe_st$st.log 2>&1; grep -E "^---|rank0 mma|rank0 producer" gpurun_out/probe_st$st.log
-done
-unset B2ME_LIB_PATH
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_spconv_tc --launch-skip 2 --launch-count 1 -o gpurun_out/prof_tc_r01d -f python tools/conv_probe.py --frames 8 --shapes 27:384:384 --reps 2 > gpurun_out/ncu_full_r01d.log 2>&1; echo "ncu rc=$?"
+timeout 300 python -m pytest tests/test_gpu_conv.py -x -q -m gpu > gpurun_out/pytest_conv.log 2>&1; echo "conv rc=$?"
+tail -3 gpurun_out/pytest_conv.log
+B2ME_LIB_PATH=$GRAFT_REPO_ROOT/markerless-robot-camera-calibration_b200/lib_debug/libb2me.so timeout 300 python tools/conv_probe.py --frames 8 --shapes 27:384:384,1:416:384 > gpurun_out/probe_x.log 2>&1; grep -E "^---|rank0 mma|rank1 relay|rank0 epi" gpurun_out/probe_x.log
+timeout 600 python tools/conv_probe.py --frames 8 --out gpurun_out/probe4.json > gpurun_out/probe4.log 2>&1; echo "rc=$?"
+tail -8 gpurun_out/probe4.log

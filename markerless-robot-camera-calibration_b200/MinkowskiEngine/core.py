@@ -82,10 +82,14 @@ def mask_sorted_perm(nbr, V, K, block_rows=None):
     (K3b keys + a device sort)."""
     if block_rows is None:
         block_rows = _State.mask_sort_block
-    keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
     ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
-    check(lib.b2me_mask_sort_keys64(ptr(nbr), V, K, block_rows, ptr(keys), ptr(ws), ws.numel(), stream()),
-          "mask_sort_keys64")
+    if block_rows == 0:  # mask-only keys fit 32 bits: half the radix passes of the device sort
+        keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
+        check(lib.b2me_mask_sort_keys(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys")
+    else:
+        keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
+        check(lib.b2me_mask_sort_keys64(ptr(nbr), V, K, block_rows, ptr(keys), ptr(ws), ws.numel(), stream()),
+              "mask_sort_keys64")
     _count(2)
     return torch.sort(keys[:V])[1].to(torch.int32)
 

@@ -733,19 +733,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     }
 }
 
-// one warp per 256-row tile pair: OR of the neighbour-occupancy masks of its rows
+// one warp per 256-row tile pair: OR of the neighbour-occupancy masks of its rows. Lane l takes rows l, l + 32, ...
+// (8 rows) and reads each row's K entries itself, so a lane has 8 K independent loads in flight.
 __global__ void __launch_bounds__(256) k_tc_tile_masks(const int32_t* __restrict__ nbr, const int32_t* __restrict__ perm,
                                                        long long V, int K, uint32_t* __restrict__ masks,
                                                        long long npairs) {
     const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= npairs) return;
     const int lane = threadIdx.x & 31;
+    long long rows[(2 * TC_BM) / 32];
+#pragma unroll
+    for (int i = 0; i < (2 * TC_BM) / 32; ++i) {
+        const long long slot = pair * (2 * TC_BM) + lane + 32 * i;
+        rows[i] = slot < V ? (perm ? (long long)__ldg(perm + slot) : slot) : -1;
+    }
     uint32_t m = 0u;
-    for (int r = 0; r < 2 * TC_BM; ++r) {
-        const long long slot = pair * (2 * TC_BM) + r;
-        if (slot >= V) break;
-        const long long row = perm ? __ldg(perm + slot) : slot;
-        if (lane < K && __ldg(nbr + row * K + lane) >= 0) m |= 1u << lane;
+#pragma unroll
+    for (int i = 0; i < (2 * TC_BM) / 32; ++i) {
+        if (rows[i] < 0) continue;
+        const int32_t* r = nbr + rows[i] * K;
+        for (int k = 0; k < K; ++k)
+            if (__ldg(r + k) >= 0) m |= 1u << k;
     }
     m = __reduce_or_sync(0xffffffffu, m);
     if (lane == 0) masks[pair] = m;

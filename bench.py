@@ -380,6 +380,9 @@ def main():
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, world, local)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -116,3 +116,51 @@ def test_lazy_fusion_launch_count(nets):
         cnet(x2).F
     # 49 convolutions + 2 head linears (maps cached): no separate BN / ReLU / add / cat kernels
     assert ME.launch_count() == 51
+
+
+def test_robotnet_full_unet_global_max_pool_parity(nets):
+    """model/robotnet.py (full UNet -> BN+ReLU -> MinkowskiGlobalMaxPooling -> MLP)."""
+    ME, _, _ = nets
+    torch.manual_seed(7)
+    MO, MC = make_models(OME), make_models(ME)
+    o = randomize_bn_stats(MO.RobotNet(3, 7)).eval()
+    c = MC.RobotNet(3, 7)
+    c.load_state_dict(o.state_dict())
+    c = c.cuda().eval()
+    pts = [_frame(seed=s)[0][:4000] * 0.25 for s in (4, 5)]
+    rgb = [_frame(seed=s)[1][:4000] for s in (4, 5)]
+    oo, _ = _run(OME, o, pts, rgb, 200.0)
+    co, _ = _run(ME, c, pts, rgb, 200.0, device="cuda")
+    assert oo.shape == (2, 7)
+    assert torch.allclose(co.cpu(), oo, atol=5e-4), float((co.cpu() - oo).abs().max())
+    ME.set_compute_dtype(torch.bfloat16)
+    try:
+        cb, _ = _run(ME, c, pts, rgb, 200.0, device="cuda")
+        assert torch.allclose(cb.cpu(), oo, atol=5e-2), float((cb.cpu() - oo).abs().max())
+    finally:
+        ME.set_compute_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("variant", ["MinkUNet50", "MinkUNet14A", "MinkUNet34C"])
+def test_other_minkunet_trunks_parity(nets, variant):
+    """Bottleneck trunks (expansion 4: 1x1 convolutions dominate, channel counts 128..1024)
+    and the other BasicBlock variants robotnet_segmentation.py:17-28 can select, on the same kernels."""
+    ME, _, _ = nets
+    torch.manual_seed(11)
+    MO, MC = make_models(OME), make_models(ME)
+    o = randomize_bn_stats(MO.RobotNetSegmentation(3, num_classes=3, variant=variant)).eval()
+    c = MC.RobotNetSegmentation(3, num_classes=3, variant=variant)
+    c.load_state_dict(o.state_dict())
+    c = c.cuda().eval()
+    pts, rgb = zip(_frame(width=96, height=72, seed=21))
+    oo, _ = _run(OME, o, pts, rgb, 100.0)
+    for dtype, tol in ((torch.float32, 1e-3), (torch.bfloat16, 3e-2)):
+        ME.set_compute_dtype(dtype)
+        try:
+            co, _ = _run(ME, c, pts, rgb, 100.0, device="cuda")
+            assert torch.equal(co.C.cpu(), oo.C)
+            err = rel_err(co.F.float().cpu(), oo.F)
+            print(f"{variant} {dtype}: logits rel err {err:.3e}")
+            assert err < tol, (variant, dtype, err)
+        finally:
+            ME.set_compute_dtype(torch.float32)

@@ -43,6 +43,9 @@
 #ifndef TC_L2_PREFETCH
 #define TC_L2_PREFETCH 1  // producers prefetch the next offset's rows into L2
 #endif
+#ifndef TC_A_COLLECTOR
+#define TC_A_COLLECTOR 0
+#endif
 #define TC_NSPLIT0 256  // N of the first MMA of a K step when the tile is wider than 256 columns
 #define TC_MAX_STAGES 8
 #define TC_MAX_SMEM 232448
@@ -224,14 +227,33 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
         "h"((uint16_t)3)
         : "memory");
 }
+// COLL: 0 = default (A discarded after use), 1 = collector::a::fill (keep the A slice in the collector buffer),
+// 2 = collector::a::lastuse (reuse the kept A slice: no second shared-memory read of A)
+template <int COLL>
 __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                  uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (COLL == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (COLL == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -437,11 +459,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
                             const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
                             for (int kk = 0; kk < kw / 16; ++kk) {
-                                tc_mma_bf16_pair(tmem_base, adesc + (uint64_t)(kk * 2), bdesc_a + (uint64_t)(kk * 2),
-                                                 idesc_a, acc);
-                                if (n_b)
-                                    tc_mma_bf16_pair(tmem_base + (uint32_t)n_a, adesc + (uint64_t)(kk * 2),
-                                                     bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
+                                if (n_b) {
+                                    // the two instructions share the A slice. Keeping it in the collector buffer
+                                    // (collector::a::fill / lastuse) was measured SLOWER on the K27 layers (863 ->
+                                    // 829 TFLOP/s), so both read A from shared memory (TC_A_COLLECTOR 0).
+                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 1 : 0>(tmem_base, adesc + (uint64_t)(kk * 2),
+                                                                             bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
+                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 2 : 0>(tmem_base + (uint32_t)n_a,
+                                                                             adesc + (uint64_t)(kk * 2),
+                                                                             bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
+                                } else {
+                                    tc_mma_bf16_pair<0>(tmem_base, adesc + (uint64_t)(kk * 2),
+                                                        bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
+                                }
                                 acc = 1u;
                             }
                             tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs

@@ -43,6 +43,9 @@
 #ifndef TC_L2_PREFETCH
 #define TC_L2_PREFETCH 1  // producers prefetch the next offset's rows into L2
 #endif
+#ifndef TC_EPI_STAGED
+#define TC_EPI_STAGED 1  // residual / output rows staged through smem for 64-byte coalesced segments (0: row per lane)
+#endif
 #ifndef TC_A_COLLECTOR
 #define TC_A_COLLECTOR 0
 #endif
@@ -67,6 +70,7 @@ struct TcParams {
     int Cin1, Cin2, nchunk1, nchunk2;
     int Cout, n_tile, n_ntiles, stages;
     int act, out_dtype, tmem_cols;
+    int acc_bufs;  // 2 when two accumulators fit TMEM (2 n_tile <= 512): the epilogue overlaps the next tile's MMAs
     float slope;
     unsigned int b_bytes;
     int total_work;  // 256-row tile pairs x n-tiles
@@ -304,10 +308,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     off += 8;
     const uint32_t bar_nbr_empty = base + off;
     off += 8;
-    const uint32_t bar_tmem_full = base + off;
-    off += 8;
-    const uint32_t bar_tmem_empty = base + off;
-    off += 8;
+    const uint32_t bar_tmem_full = base + off;   // [2] one per accumulator buffer
+    off += 16;
+    const uint32_t bar_tmem_empty = base + off;  // [2]
+    off += 16;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + off);
 
     // ---- one-time setup
@@ -319,8 +323,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         }
         mbar_init(bar_nbr_full, 2);            // 2 prefetch warps
         mbar_init(bar_nbr_empty, 4);           // 4 producer warps
-        mbar_init(bar_tmem_full, 1);           // tcgen05.commit (multicast from the leader)
-        mbar_init(bar_tmem_empty, 2 * TC_EPI_WARPS);  // epilogue warps of both CTAs (leader's barrier only)
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tmem_full + 8 * b, 1);                  // tcgen05.commit (multicast from the leader)
+            mbar_init(bar_tmem_empty + 8 * b, 2 * TC_EPI_WARPS);  // epilogue warps of both CTAs (leader's barrier)
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -435,8 +441,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             for (int w = unit0; w < p.total_work; w += G, ++it) {
                 const uint32_t kmask = kmask_next;
                 if (w + G < p.total_work) kmask_next = tile_mask(w + G);
-                if (it > 0) {  // both CTAs' epilogues of the previous tile pair must have drained their accumulators
-                    PROF(2, mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u));
+                // accumulator buffer of this work item and how often it has been used before
+                const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
+                const int au = p.acc_bufs == 2 ? (it >> 1) : it;
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * p.n_tile);
+                if (au > 0) {  // both CTAs' epilogues must have drained the previous tile of this buffer
+                    PROF(2, mbar_wait(bar_tmem_empty + 8 * ab, (uint32_t)(au - 1) & 1u));
                     tc_fence_after();
                 }
                 uint32_t acc = 0u;
@@ -463,13 +473,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                                     // the two instructions share the A slice. Keeping it in the collector buffer
                                     // (collector::a::fill / lastuse) was measured SLOWER on the K27 layers (863 ->
                                     // 829 TFLOP/s), so both read A from shared memory (TC_A_COLLECTOR 0).
-                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 1 : 0>(tmem_base, adesc + (uint64_t)(kk * 2),
+                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 1 : 0>(tmem_acc, adesc + (uint64_t)(kk * 2),
                                                                              bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
-                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 2 : 0>(tmem_base + (uint32_t)n_a,
+                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 2 : 0>(tmem_acc + (uint32_t)n_a,
                                                                              adesc + (uint64_t)(kk * 2),
                                                                              bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
                                 } else {
-                                    tc_mma_bf16_pair<0>(tmem_base, adesc + (uint64_t)(kk * 2),
+                                    tc_mma_bf16_pair<0>(tmem_acc, adesc + (uint64_t)(kk * 2),
                                                         bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
                                 }
                                 acc = 1u;
@@ -483,7 +493,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
-                if (lane == 0) tc_commit_pair(bar_tmem_full);  // accumulators of both CTAs are complete
+                if (lane == 0) tc_commit_pair(bar_tmem_full + 8 * ab);  // accumulators of both CTAs are complete
                 __syncwarp();
             }
 #ifdef B2ME_TC_PROFILE
@@ -583,7 +593,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // the column half e >> 2 of the tile
         const int ew = warp - 8;
         const int we = ew & 3, chalf = ew >> 2;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(we * 32) << 16);
+        const uint32_t lane_addr0 = tmem_base + ((uint32_t)(we * 32) << 16);
         const uint32_t stg = stage_out + (uint32_t)ew * TC_STAGE_OUT_BYTES;
         // staging image: row r (0..31) = 64 bytes, 16-byte piece q stored at q ^ ((r >> 1) & 3): conflict-free for both
         // the row-per-lane view (lane = row) and the coalesced view (4 lanes per row, 8 rows per access)
@@ -599,6 +609,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         for (int w = unit0; w < p.total_work; w += G, ++it) {
             const int tile_p = w / p.n_ntiles;
             const int n0 = (w - tile_p * p.n_ntiles) * p.n_tile;
+            const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
+            const uint32_t au_par = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it) & 1u;
+            const uint32_t lane_addr = lane_addr0 + (uint32_t)(ab * p.n_tile);
+            const uint32_t bar_tf = bar_tmem_full + 8 * ab, bar_te = bar_tmem_empty + 8 * ab;
             const long long slot = ((long long)tile_p * 2 + rank) * TC_BM + we * 32 + lane;
             const int row = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
             int crows[4];  // output rows of the coalesced view
@@ -608,6 +622,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             if (p.out_dtype == B2ME_BF16) {
                 const __nv_bfloat16* resp = p.residual;
                 __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#if TC_EPI_STAGED
                 uint4 R[4];
                 auto load_res = [&](int cb) {  // coalesced: 64-byte segment of 8 rows per access
                     const int cw = min(32, p.n_tile - cb);
@@ -620,14 +635,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     }
                 };
                 if (resp && c_lo < c_hi) load_res(c_lo);
-                PROF(1, mbar_wait(bar_tmem_full, (uint32_t)it & 1u));
+                PROF(1, mbar_wait(bar_tf, au_par));
                 tc_fence_after();
 #ifdef B2ME_TC_PROFILE
                 const long long t_epi0 = clock64();
 #endif
                 if (c_lo >= c_hi) {  // narrow tile: this warp has no columns
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
+                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
                 }
                 for (int cb = c_lo; cb < c_hi; cb += 32) {
                     const int cw = min(32, p.n_tile - cb);
@@ -652,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     if (cb + 32 >= c_hi) {  // this warp's part of the accumulator is read: release it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);  // the leader's barrier
+                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);  // the leader's barrier
                     }
                     float v[32];
 #pragma unroll
@@ -700,19 +715,101 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     }
                     __syncwarp();  // staging is reused by the next chunk
                 }
+#else
+                uint4 R[4];
+                // row-per-lane epilogue (TC_EPI_STAGED 0): every lane loads / stores the 64 contiguous bytes of ITS row per
+                // 32-column chunk, no shared-memory round trip. Measured 10-60 % SLOWER than the staged variant (32
+                // half-used sectors per store instruction), kept for experiments only.
+                const long long rbase_o = (long long)(row >= 0 ? row : 0) * p.Cout + n0;
+                auto load_res = [&](int cb) {
+                    const int cw = min(32, p.n_tile - cb);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        R[m] = make_uint4(0u, 0u, 0u, 0u);
+                        if (row >= 0 && m * 8 < cw)
+                            R[m] = __ldg(reinterpret_cast<const uint4*>(resp + rbase_o + cb + m * 8));
+                    }
+                };
+                if (resp && c_lo < c_hi) load_res(c_lo);
+                PROF(1, mbar_wait(bar_tf, au_par));
+                tc_fence_after();
+#ifdef B2ME_TC_PROFILE
+                const long long t_epi0 = clock64();
+#endif
+                if (c_lo >= c_hi) {  // narrow tile: this warp has no columns
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
+                }
+                for (int cb = c_lo; cb < c_hi; cb += 32) {
+                    const int cw = min(32, p.n_tile - cb);
+                    uint32_t r[32];
+                    if (cw == 32) {
+                        tmem_ld_x32(lane_addr + (uint32_t)cb, r);
+                    } else {
+                        tmem_ld_x16(lane_addr + (uint32_t)cb, r);
+#pragma unroll
+                        for (int q = 16; q < 32; ++q) r[q] = 0u;
+                    }
+                    uint4 Rc[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) Rc[m] = R[m];
+                    if (resp && cb + 32 < c_hi) load_res(cb + 32);  // in flight during this chunk's math and stores
+                    tmem_ld_wait();
+                    if (cb + 32 >= c_hi) {  // this warp's part of the accumulator is read: release it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);  // the leader's barrier
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
+                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
+                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                        v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                        v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                        v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                        v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
+                    }
+                    if (resp) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint32_t wv[4] = {Rc[q4].x, Rc[q4].y, Rc[q4].z, Rc[q4].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
+                                v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = apply_act(v[q4 * 8 + 2 * e], p.act, p.slope);
+                            const float x1 = apply_act(v[q4 * 8 + 2 * e + 1], p.act, p.slope);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        if (row >= 0 && q4 * 8 < cw)
+                            *reinterpret_cast<uint4*>(outp + rbase_o + cb + q4 * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+#endif
 #ifdef B2ME_TC_PROFILE
                 prof_[2] += (unsigned long long)(clock64() - t_epi0);
                 ++prof_[7];
 #endif
             } else {
                 // fp32 rows (parity tests only): row-per-lane stores, 16-column chunks split between the two halves
-                mbar_wait(bar_tmem_full, (uint32_t)it & 1u);
+                mbar_wait(bar_tf, au_par);
                 tc_fence_after();
                 const int n16 = p.n_tile >> 4;
                 const int q_lo = chalf ? (n16 + 1) >> 1 : 0, q_hi = chalf ? n16 : (n16 + 1) >> 1;
                 if (q_lo >= q_hi) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
+                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
                 }
                 for (int qc = q_lo; qc < q_hi; ++qc) {
                     const int cb = qc * 16;
@@ -722,7 +819,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     if (qc + 1 >= q_hi) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_tmem_empty, 0u);
+                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);
                     }
                     if (row < 0) continue;
                     float v[16];
@@ -801,16 +898,23 @@ extern "C" int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static int tc_n_tile(int Cout) {
-    if (Cout <= 384) return Cout;
-    return 256;
+// Output-channel tile. K = 27 (many items per tile): the widest tile TMEM takes (<= 384 columns), so that the gathered
+// rows are read once (K = 8 too: measured). K = 1 (few items per tile, contiguous A): tiles of <= 256 columns so that
+// two accumulators fit the 512 TMEM columns and the epilogue overlaps the next tile's MMAs.
+static int tc_n_tile(int K, int Cout) {
+    if (Cout <= 256) return Cout;
+    if (K != 1 && Cout <= 384) return Cout;
+    if (Cout % 256 == 0) return 256;
+    if (Cout % 192 == 0) return 192;
+    if (Cout % 128 == 0) return 128;
+    return Cout <= 384 ? Cout : 0;
 }
 
 extern "C" int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout) {
     if ((K != 1 && K != 8 && K != 27) || Cin1 < 16 || Cin2 < 0 || Cout < 16 || Cout > 1024) return 0;
     if (Cin1 % 16 || Cin2 % 16 || Cout % 16) return 0;
-    const int nt = tc_n_tile(Cout);
-    if (Cout % nt) return 0;
+    const int nt = tc_n_tile(K, Cout);
+    if (nt <= 0 || Cout % nt) return 0;
     if (nt > 256 && ((nt - TC_NSPLIT0) % 16 || nt - TC_NSPLIT0 < 32)) return 0;
     return 1;
 }
@@ -869,7 +973,7 @@ extern "C" int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, i
                                     b2me_stream_t stream) {
     if (!W || !packed) return B2ME_EINVAL;
     if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
-    const int nt = tc_n_tile(Cout);
+    const int nt = tc_n_tile(K, Cout);
     const int nchunk1 = (Cin1 + TC_BK - 1) / TC_BK, nchunk2 = (Cin2 + TC_BK - 1) / TC_BK;
     const long long total = (long long)(Cout / nt) * K * (nchunk1 + nchunk2) * nt * 8;
     k_tc_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -936,21 +1040,22 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.nchunk1 = (Cin1 + TC_BK - 1) / TC_BK;
     p.nchunk2 = (Cin2 + TC_BK - 1) / TC_BK;
     p.Cout = Cout;
-    p.n_tile = tc_n_tile(Cout);
+    p.n_tile = tc_n_tile(K, Cout);
     p.n_ntiles = Cout / p.n_tile;
     p.act = act;
     p.out_dtype = out_dtype;
     p.slope = slope;
     p.b_bytes = (unsigned)(p.n_tile / 2) * 128u;  // each CTA of the pair stages half of every weight tile
+    p.acc_bufs = 2 * p.n_tile <= 512 ? 2 : 1;
     int cols = 32;
-    while (cols < p.n_tile) cols <<= 1;
+    while (cols < p.acc_bufs * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
     const int64_t work = ceil_div64(V_out, 2 * TC_BM) * p.n_ntiles;  // 256-row tile pairs x n-tiles
     if (work > 0x7fffffff) return B2ME_EUNSUPPORTED;
     p.total_work = (int)work;
 
     const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 +
-                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 4 * 8 + 16;
+                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 6 * 8 + 16;
     const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
     int S = TC_MAX_STAGES;
     while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;

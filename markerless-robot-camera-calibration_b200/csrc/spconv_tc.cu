@@ -43,6 +43,10 @@
 #ifndef TC_L2_PREFETCH
 #define TC_L2_PREFETCH 1  // producers prefetch the next offset's rows into L2
 #endif
+#ifndef TC_GI
+#define TC_GI 1  // (offset, chunk) items per stage = per barrier round. 2 (fewer, larger rounds; 2 stages at n_tile 384) measured slower: 776 vs 837 TFLOP/s
+#endif
+static_assert(TC_GI == 1 || TC_GI == 2, "the B loader announces 1 or TC_GI items per group");
 #ifndef TC_EPI_STAGED
 #define TC_EPI_STAGED 1  // residual / output rows staged through smem for 64-byte coalesced segments (0: row per lane)
 #endif
@@ -74,6 +78,7 @@ struct TcParams {
     float slope;
     unsigned int b_bytes;
     int total_work;  // 256-row tile pairs x n-tiles
+    int debug;       // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
 };
 
 // Optional in-kernel role timers (build with -DB2ME_TC_PROFILE; tools/conv_probe.py): cycles that lane 0 of each
@@ -289,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
     // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 8 x 2 KB][barriers][tmem ptr]
-    uint32_t off = (uint32_t)S * stage_bytes;
+    uint32_t off = (uint32_t)(S * TC_GI) * stage_bytes;  // S stages of TC_GI items
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
     off += TC_BM * KT * 4;
     off = (off + 15u) & ~15u;
@@ -359,7 +364,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // =============================== gather producers ===============================
         const int j = tid & 7;        // 16-byte piece inside the 128-byte row
         const int rbase = tid >> 3;   // rows rbase + 16*i
-        int ist = 0, iph = 0;         // stage / phase of the next item to issue
+        int ist = 0, iph = 0;         // stage / phase of the next group of items to issue
+        int isub = 0;                 // item slot inside the group (a stage holds TC_GI items)
         int it = 0;
         PROF_DECL
         const long long t_role0 = clock64();
@@ -395,15 +401,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
-                    PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
-                    PROF_COUNT(7);
+                    if (isub == 0) {
+                        PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
+                        PROF_COUNT(7);
+                    }
                     const __nv_bfloat16* src;
                     int cin, coff;
                     if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
                     else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * TC_BK; }
                     const int kw = min(TC_BK, cin - coff);
-                    if (j * 8 < kw) {
-                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes;
+                    if (j * 8 < kw && !(p.debug & 1)) {
+                        const uint32_t a_s = base + (uint32_t)(ist * TC_GI + isub) * stage_bytes;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = rbase + 16 * i;
@@ -413,10 +421,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             cp_async_16(dst, g, id >= 0 ? 16u : 0u);
                         }
                     }
-                    // asynchronous publication: this thread's arrival fires when its copies have landed, so the
-                    // producers run ahead as far as the ring allows and never wait for their own gathers
-                    cp_async_mbar_arrive_noinc(bar_full + 8 * ist);
-                    if (++ist == S) { ist = 0; iph ^= 1; }
+                    const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
+                    if (++isub == TC_GI || tile_last) {
+                        // asynchronous publication: this thread's arrival fires when its copies have landed, so the
+                        // producers run ahead as far as the ring allows and never wait for their own gathers
+                        cp_async_mbar_arrive_noinc(bar_full + 8 * ist);
+                        isub = 0;
+                        if (++ist == S) { ist = 0; iph ^= 1; }
+                    }
                 }
             }
         }
@@ -450,25 +462,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     tc_fence_after();
                 }
                 uint32_t acc = 0u;
+                int sub = 0;
                 for (int k = 0; k < KT; ++k) {
                     if (!((kmask >> k) & 1u)) continue;
                     for (int c = 0; c < nchunk; ++c) {
                         const int kw = (c < p.nchunk1) ? min(TC_BK, p.Cin1 - c * TC_BK)
                                                        : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
-                        PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
-                        PROF_COUNT(7);
+                        if (sub == 0) {
+                            PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
+                            PROF_COUNT(7);
+                        }
 #ifdef B2ME_TC_PROFILE
                         pt_ = clock64();
 #endif
+                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
+                        const bool group_last = (sub + 1 == TC_GI) || tile_last;
                         if (lane == 0) {
-                            fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
-                            tc_fence_after();
-                            const uint32_t a_s = base + (uint32_t)st * stage_bytes;
+                            if (sub == 0) {
+                                fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
+                                tc_fence_after();
+                            }
+                            const uint32_t a_s = base + (uint32_t)(st * TC_GI + sub) * stage_bytes;
                             const uint32_t b_s = a_s + TC_A_BYTES;
                             const uint64_t adesc = make_smem_desc_sw128(a_s);
                             const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
                             const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
-                            for (int kk = 0; kk < kw / 16; ++kk) {
+                            for (int kk = 0; kk < ((p.debug & 4) ? 0 : kw / 16); ++kk) {
                                 if (n_b) {
                                     // the two instructions share the A slice. Keeping it in the collector buffer
                                     // (collector::a::fill / lastuse) was measured SLOWER on the K27 layers (863 ->
@@ -484,13 +503,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                                 }
                                 acc = 1u;
                             }
-                            tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
+                            if (group_last) tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
                         }
-                        __syncwarp();
+                        if (group_last) {
+                            __syncwarp();
+                            sub = 0;
+                            if (++st == S) { st = 0; ph ^= 1; }
+                        } else {
+                            ++sub;
+                        }
 #ifdef B2ME_TC_PROFILE
                         prof_[5] += (unsigned long long)(clock64() - pt_);
 #endif
-                        if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
                 if (lane == 0) tc_commit_pair(bar_tmem_full + 8 * ab);  // accumulators of both CTAs are complete
@@ -510,9 +534,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             for (int w = unit0; w < p.total_work; w += G) {
                 const uint32_t kmask = kmask_next;
                 if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+                int sub = 0;
                 for (int k = 0; k < KT; ++k) {
                     if (!((kmask >> k) & 1u)) continue;
                     for (int c = 0; c < nchunk; ++c) {
+                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
+                        if (++sub < TC_GI && !tile_last) continue;
+                        sub = 0;
                         PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
                         PROF_COUNT(7);
                         if (lane == 0) {
@@ -538,19 +566,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 const uint32_t kmask = kmask_next;
                 if (w + G < p.total_work) kmask_next = tile_mask(w + G);
                 const int nt = w % p.n_ntiles;
+                int sub = 0;
                 for (int k = 0; k < KT; ++k) {
                     if (!((kmask >> k) & 1u)) continue;
                     for (int c = 0; c < nchunk; ++c) {
-                        mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
+                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
+                        if (sub == 0) mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
                         if (lane == 0) {
-                            const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
+                            const uint32_t b_s = base + (uint32_t)(st * TC_GI + sub) * stage_bytes + TC_A_BYTES;
                             const uint8_t* g =
                                 p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
-                            mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
-                            bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
+                            if (p.debug & 2) {
+                                if (sub == 0) mbar_arrive(bar_full + 8 * st);
+                            } else {
+                                // one arrive per group, announcing the bytes of all its items (1 or TC_GI)
+                                if (sub == 0)
+                                    mbar_arrive_expect_tx(bar_full + 8 * st, tile_last ? p.b_bytes : TC_GI * p.b_bytes);
+                                bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
+                            }
                         }
-                        __syncwarp();
-                        if (++st == S) { st = 0; ph ^= 1; }
+                        if (++sub == TC_GI || tile_last) {
+                            __syncwarp();
+                            sub = 0;
+                            if (++st == S) { st = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -1056,11 +1095,13 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
 
     const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 +
                          (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 6 * 8 + 16;
-    const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
+    const size_t stage_bytes = (size_t)TC_GI * (TC_A_BYTES + p.b_bytes);  // a stage holds TC_GI items
     int S = TC_MAX_STAGES;
-    while (S >= 3 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
-    if (S < 3) return B2ME_EUNSUPPORTED;
+    while (S >= 2 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
+    if (S < 2) return B2ME_EUNSUPPORTED;
+    p.debug = 0;
 #ifdef B2ME_TC_PROFILE
+    if (const char* e = getenv("B2ME_TC_DEBUG")) p.debug = atoi(e);
     if (const char* e = getenv("B2ME_TC_STAGES")) {  // debug build only: ring-depth experiments
         const int want = atoi(e);
         if (want >= 2 && want < S) S = want;

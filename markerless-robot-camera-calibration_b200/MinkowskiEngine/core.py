@@ -40,6 +40,7 @@ class SparseTensorOperationMode(Enum):
 
 class _State:
     mask_sort = True  # tcgen05 convolutions take a neighbour-mask-sorted row permutation (tile-level offset skipping)
+    mask_sort_min_rows = 32768  # smaller maps keep their natural row order (the sort costs more than it saves)
     mask_sort_block = 0  # rows per locality block of that sort, 0 = whole map (measured: 0 is fastest)
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
@@ -211,7 +212,7 @@ class CoordinateManager:
         lv = self.levels[key]
         if lv.perm_k3 is None:
             nbr = self.kernel_map_k3(key)
-            perm = mask_sorted_perm(nbr, lv.V, 27) if _State.mask_sort else None
+            perm = mask_sorted_perm(nbr, lv.V, 27) if (_State.mask_sort and lv.V >= _State.mask_sort_min_rows) else None
             lv.perm_k3 = (perm, tile_masks(nbr, perm, lv.V, 27))
         return lv.perm_k3
 
@@ -220,7 +221,8 @@ class CoordinateManager:
         name = "perm_" + which
         if rec.get(name) is None:
             nbr = rec["nbr_" + which]
-            perm = mask_sorted_perm(nbr, nbr.shape[0], 8) if _State.mask_sort else None
+            perm = (mask_sorted_perm(nbr, nbr.shape[0], 8)
+                    if (_State.mask_sort and nbr.shape[0] >= _State.mask_sort_min_rows) else None)
             rec[name] = (perm, tile_masks(nbr, perm, nbr.shape[0], 8))
         return rec[name]
 

@@ -31,7 +31,7 @@ from MinkowskiEngine.core import _count
 from . import output as out_utils
 from .icp import icp_p2p_batched
 from .synthetic import REFERENCE_KEY_POINTS
-from .transformation import (rigid_transform_3D_batched, get_pose_from_matrix, get_base2cam_pose)
+from .transformation import (rigid_transform_3D_batched, get_poses_from_matrices, get_base2cam_pose)
 
 
 @dataclass
@@ -285,7 +285,7 @@ class BatchedInferenceEngine:
             if stats is not None:
                 res["icp_stats"] = host[:, c:c + 4]
                 c += 4
-            res["ee_pose"] = np.stack([get_pose_from_matrix(T) for T in res["ee_T"]])
+            res["ee_pose"] = get_poses_from_matrices(res["ee_T"])
             if kp_T is not None:
                 res["kp_T"] = host[:, c:c + 16].reshape(S, 4, 4)
                 res["kp_valid"] = host[:, c + 16] > 0.5
@@ -296,7 +296,7 @@ class BatchedInferenceEngine:
                 c += 2 * K + 1
                 if kstats is not None:
                     res["kp_icp_stats"] = host[:, c:c + 4]
-                res["kp_pose"] = np.stack([get_pose_from_matrix(T) for T in res["kp_T"]])
+                res["kp_pose"] = get_poses_from_matrices(res["kp_T"])
         return res
 
     @torch.no_grad()

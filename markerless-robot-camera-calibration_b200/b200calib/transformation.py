@@ -54,6 +54,15 @@ def get_pose_from_matrix(trans_mat):
     return np.concatenate((trans_mat[:3, 3], get_q_from_matrix(trans_mat[:3, :3])))
 
 
+def get_poses_from_matrices(trans_mats):
+    """batched get_pose_from_matrix: [S,4,4] -> [S,7] (x,y,z,qw,qx,qy,qz), one SciPy call for all frames."""
+    T = np.asarray(trans_mats, dtype=np.float64)
+    if len(T) == 0:
+        return np.zeros((0, 7))
+    q = Rotation.from_matrix(T[:, :3, :3].copy()).as_quat()  # x,y,z,w
+    return np.concatenate((T[:, :3, 3], q[:, 3:], q[:, :3]), axis=1)
+
+
 def get_pose_inverse(pose):
     return get_pose_from_matrix(get_transformation_matrix_inverse(get_transformation_matrix(pose)))
 

@@ -94,6 +94,65 @@ k_spconv_simt(const void* __restrict__ in1, int Cin1, const void* __restrict__ i
     }
 }
 
+// Stem variant (conv0p1s1: Cin = 3, Cout = 32, K = 27, fp32 point features): one thread per output row keeps the 32
+// accumulators in registers, the 27 x Cin x 32 weights sit in shared memory (broadcast reads), absent neighbours are
+// skipped. Same summation order (k, then c) as the generic kernel: bit-identical results.
+#define STEM_COUT 32
+__global__ void __launch_bounds__(256)
+k_spconv_stem(const float* __restrict__ in, int Cin, const float* __restrict__ W, const int32_t* __restrict__ nbr, int K,
+              int64_t V_out, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope,
+              void* __restrict__ out, int out_dtype) {
+    extern __shared__ __align__(16) float stem_w[];  // [K * Cin][32]
+    for (int i = threadIdx.x; i < K * Cin * STEM_COUT; i += blockDim.x) stem_w[i] = W[i];
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < V_out;
+         row += (int64_t)gridDim.x * blockDim.x) {
+        float acc[STEM_COUT];
+#pragma unroll
+        for (int n = 0; n < STEM_COUT; ++n) acc[n] = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const int64_t id = nbr ? (int64_t)__ldg(nbr + row * K + k) : row;
+            if (id < 0) continue;
+            for (int c = 0; c < Cin; ++c) {
+                const float x = __ldg(in + id * Cin + c);
+                const float4* w = reinterpret_cast<const float4*>(stem_w + (k * Cin + c) * STEM_COUT);
+#pragma unroll
+                for (int q = 0; q < STEM_COUT / 4; ++q) {
+                    const float4 wv = w[q];
+                    acc[4 * q + 0] = fmaf(x, wv.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(x, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(x, wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(x, wv.w, acc[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < STEM_COUT; ++n) {
+            float v = acc[n];
+            if (scale) v *= scale[n];
+            if (shift) v += shift[n];
+            acc[n] = apply_act(v, act, slope);
+        }
+        if (out_dtype == B2ME_BF16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row * STEM_COUT);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t wv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(acc[q * 8 + 2 * e], acc[q * 8 + 2 * e + 1]);
+                    wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                op[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            }
+        } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * STEM_COUT);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+    }
+}
+
 extern "C" int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, int Cin2, int in_dtype,
                                     const float* W, const int32_t* nbr, int K, int64_t V_out, int Cout,
                                     const float* scale, const float* shift, const void* residual, int res_dtype,
@@ -102,6 +161,15 @@ extern "C" int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, 
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
     if (V_out == 0) return B2ME_OK;
+    if (Cin2 == 0 && Cin1 <= 4 && Cout == STEM_COUT && K <= 27 && in_dtype == B2ME_F32 && !residual) {
+        int64_t blocks = ceil_div64(V_out, 256);
+        if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+        const size_t smem = (size_t)K * Cin1 * STEM_COUT * sizeof(float);
+        k_spconv_stem<<<(unsigned)blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float*>(in1), Cin1, W, nbr, K, V_out, scale, shift, act, slope, out, out_dtype);
+        B2ME_CHECK_LAUNCH();
+        return B2ME_OK;
+    }
     dim3 grid((unsigned)ceil_div64(V_out, SM_BM), (unsigned)((Cout + SM_BN - 1) / SM_BN));
     k_spconv_simt<<<grid, SM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         in1, Cin1, in2, Cin2, in_dtype, W, nbr, K, V_out, Cout, scale, shift, residual, res_dtype, act, slope, out,

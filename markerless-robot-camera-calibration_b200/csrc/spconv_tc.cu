@@ -53,7 +53,9 @@ static_assert(TC_GI == 1 || TC_GI == 2, "the B loader announces 1 or TC_GI items
 #ifndef TC_A_COLLECTOR
 #define TC_A_COLLECTOR 0
 #endif
+#ifndef TC_NSPLIT0
 #define TC_NSPLIT0 256  // N of the first MMA of a K step when the tile is wider than 256 columns
+#endif
 #define TC_MAX_STAGES 8
 #define TC_MAX_SMEM 232448
 #define TC_MIN_SMEM (120 * 1024)  // more than half an SM: one CTA per SM, so a 512-column TMEM alloc never blocks

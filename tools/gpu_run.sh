@@ -1,6 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest15.log 2>&1; echo "all rc=$?"
-tail -3 gpurun_out/pytest15.log
-timeout 600 python bench.py --frames 32 --steps 3 --warmup 3 --no-cpu-baseline --stages > gpurun_out/bench_v9_32.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_v9_32.log | cut -c1-200
+timeout 900 python bench.py --frames 16 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain_r01f.log 2>&1; echo "rc=$?"
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/launches_r01f.csv python bench.py --frames 16 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_r01f.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spconv_tc --launch-skip 42 --launch-count 3 -o gpurun_out/prof_tc_r01f -f python bench.py --frames 16 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_r01f.log 2>&1; echo "ncu full rc=$?"

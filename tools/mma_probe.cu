@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
     const uint32_t base = (raw + 1023u) & ~1023u;
     __shared__ uint64_t bar;
     __shared__ uint64_t bar2[8];
+    __shared__ uint64_t bar3;
     __shared__ uint32_t tmem_ptr;
     uint32_t rank = 0;
     if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&bar), 1);
         for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar2[i]), 1);
+        mbar_init(smem_u32(&bar3), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -130,6 +132,18 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
             }
             if (commit_each & 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (commit_each & 1) commit<CG>(smem_u32(&bar2[r % distinct_stages]));
+            if (commit_each & 8) {   // a plain shared-memory poll between items
+                uint32_t v;
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&tmem_ptr)) : "memory");
+                if (v == 0xdeadbeefu) acc = 0;
+            }
+            if (commit_each & 16) {  // an mbarrier check on a phase that completed long ago (parity 1 of a fresh barrier)
+                uint32_t ok;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar3)), "r"(1u) : "memory");
+                if (!ok) acc = 0;
+            }
+            if (commit_each & 32) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const long long t1 = clock64();
         commit<CG>(smem_u32(&bar));
@@ -183,12 +197,7 @@ static void run(int n_a, int n_b, int grid, int stages, int commit_each) {
 }
 
 int main() {
-    for (int ce : {0, 4}) {
-        run<2>(256, 128, 2, 3, ce);
-        run<2>(128, 128, 2, 3, ce);
-        run<2>(64, 64, 2, 3, ce);
-        run<2>(32, 0, 2, 3, ce);
-        run<1>(64, 64, 2, 3, ce);
-    }
+    // bits: 1 commit per item, 2 fence.proxy.async, 8 shared-memory poll, 16 mbarrier test_wait, 32 tcgen05.fence::after
+    for (int ce : {0, 1, 3, 1 + 8, 1 + 16, 1 + 32, 1 + 2 + 16 + 32}) run<2>(256, 128, 2, 3, ce);
     return 0;
 }

@@ -85,3 +85,46 @@ def test_predict_batch_predicted_crop_and_empty(setup):
     raw = ref["segmentation_raw"]
     decided = raw["margin"] > 1e-4 * raw["scale"]
     assert np.array_equal(res[2].segmentation[decided], ref["segmentation"][decided])
+
+
+def test_full_size_batch_independence_and_determinism():
+    """BASELINE.json configs[1] size (640x480 frames, 5 mm voxels, bf16 tcgen05 path), size-independent properties:
+    (1) the per-point labels and voxel logits of a frame do not depend on which other frames share its batch (every
+        output row is an independent fp32 accumulation in a fixed (offset, chunk) order, whatever the tile layout),
+    (2) two runs of the same batch are bit-identical (no atomics / scatter in the convolution),
+    (3) the voxel count of the batch is the sum of the per-frame counts and coordinates stay frame-sorted."""
+    import MinkowskiEngine as ME
+    from b200calib.models import make_models, randomize_bn_stats
+    from b200calib.synthetic import make_frame
+    from b200calib.pipeline import segment_points, normalize_colors_
+    torch.manual_seed(13)
+    net = randomize_bn_stats(make_models(ME).RobotNetSegmentation(3, num_classes=3)).cuda().eval()
+    frames = [make_frame(900 + i) for i in range(3)]
+    ME.set_compute_dtype(torch.bfloat16)
+    try:
+        def run(sel):
+            pts = torch.from_numpy(np.concatenate([frames[i]["points"] for i in sel])).cuda()
+            rgb = torch.from_numpy(np.concatenate([frames[i]["rgb"] for i in sel])).cuda()
+            bidx = torch.from_numpy(np.concatenate([np.full(len(frames[i]["points"]), j, np.float32)
+                                                    for j, i in enumerate(sel)])).cuda()
+            with torch.no_grad():
+                labels, fld, out = segment_points(net, pts, normalize_colors_(rgb), bidx, len(sel), 200.0)
+            return labels.cpu(), out.F.float().cpu(), out.C.cpu()
+        lab_all, log_all, C_all = run([0, 1, 2])
+        lab_again, log_again, _ = run([0, 1, 2])
+        assert torch.equal(lab_all, lab_again) and torch.equal(log_all, log_again), "two runs differ"
+        assert torch.all(C_all[1:, 0] >= C_all[:-1, 0]), "voxel rows are frame-sorted (first-occurrence order)"
+        n_off = np.concatenate(([0], np.cumsum([len(f["points"]) for f in frames])))
+        v_total = 0
+        for i in range(3):
+            lab_i, log_i, C_i = run([i])
+            rows = (C_all[:, 0] == i).nonzero().flatten()
+            assert len(rows) == len(C_i)
+            assert torch.equal(C_all[rows][:, 1:], C_i[:, 1:])
+            assert torch.equal(log_all[rows], log_i), f"frame {i}: logits depend on the batch composition"
+            assert torch.equal(lab_all[n_off[i]:n_off[i + 1]], lab_i)
+            v_total += len(C_i)
+        assert v_total == len(C_all)
+        assert len(C_all) > 600000  # full-size: ~280 k voxels per frame
+    finally:
+        ME.set_compute_dtype(torch.float32)

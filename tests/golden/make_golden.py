@@ -91,9 +91,44 @@ def main():
     c, off = P.center_at_origin(pts)
     out.update(pre_pts=pts, pre_centered=c, pre_offset=off, pre_rgb255=rgb255, pre_rgb255_out=P.normalize_colors(rgb255),
                pre_rgb01=rgb01, pre_rgb01_out=P.normalize_colors(rgb01))
+    # ---- per-point heads: the reference's own utils/output.py (:45-87) and utils/metrics.py (:110-127), imported with
+    #      this repo's oracle package standing in for `MinkowskiEngine` (output.py only uses it in a type annotation)
+    import torch
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    import oracle.MinkowskiEngine as OME
+    sys.modules["MinkowskiEngine"] = OME
+    from utils import output as RO
+    from utils import metrics as RM
+    g = torch.Generator().manual_seed(13)
+    kp_logits = torch.randn(700, 6, generator=g) * 6.0
+    kp_logits[:, 3] = kp_logits[:, 3] * 0.05 - 3.0    # a class that never gets confident
+    idx75, cls75, pr75 = RO.get_key_point_predictions(kp_logits, 0.75)
+    idx999, cls999, pr999 = RO.get_key_point_predictions(kp_logits, 0.999)
+    kp10_logits = torch.randn(900, 10, generator=g) * 9.0
+    idx10, cls10, pr10 = RO.get_key_point_predictions(kp10_logits, 0.75)
+    vote_out = torch.randn(1200, 2, generator=g)
+    vote_coords = rng.normal(0, 0.1, (1200, 3)).astype(np.float32)
+    vote_q = quats[3].astype(np.float32)
+    vc_plain = RO.get_pred_center(vote_out, vote_coords.copy(), ee_r=0.02, q=None)
+    vc_q = RO.get_pred_center(vote_out, vote_coords.copy(), ee_r=0.02, q=vote_q)
+    seg_logits = torch.randn(5000, 3, generator=g)
+    seg_logits[::7, 1] = seg_logits[::7, 0]           # exact ties: torch.max returns the lowest index
+
+    class _Field:
+        features = seg_logits
+    seg_preds, seg_conf = RO.get_segmentations_from_tensor_field(_Field())
+    pm = [RM.compute_pose_metrics(a.copy(), b.copy()) for a, b in zip(poses, poses2)]
+    out.update(kp_logits=kp_logits.numpy(), kp_idx75=idx75, kp_cls75=cls75, kp_pr75=pr75.numpy(), kp_idx999=idx999,
+               kp_cls999=cls999, kp_pr999=pr999.numpy(), kp10_logits=kp10_logits.numpy(), kp10_idx=idx10,
+               kp10_cls=cls10, kp10_pr=pr10.numpy(), vote_out=vote_out.numpy(), vote_coords=vote_coords,
+               vote_q=vote_q, vote_center=np.asarray(vc_plain), vote_center_q=np.asarray(vc_q),
+               seg_logits=seg_logits.numpy(), seg_preds=seg_preds, seg_conf=seg_conf,
+               metric_dist=np.array([m["dist_position"] for m in pm]),
+               metric_angle=np.array([m["angle_diff"] for m in pm]))
     np.savez_compressed(os.path.join(HERE, "reference_geometry.npz"), **out)
 
     # ---- CAD input fixture: xyz of app/hand_files/hand.pcd (4480 points), read with our PCD reader
+    sys.modules.pop("MinkowskiEngine", None)   # the alias above must not shadow the CUDA package b200calib imports
     sys.path.insert(0, os.path.join(HERE, "..", "..", "markerless-robot-camera-calibration_b200"))
     from b200calib.icp import read_pcd_xyz
     cad = read_pcd_xyz(os.path.join(REF, "app", "hand_files", "hand.pcd"))

@@ -90,3 +90,32 @@ def test_global_pool_and_slice():
         yo = relu_o(obn(o)) + o
     assert torch.allclose(yc.F.cpu(), yo.F, atol=1e-5)
     assert torch.allclose(ME.cat(yc, c).F.cpu(), OME.cat(yo, o).F, atol=1e-5)
+
+
+def test_heads_vs_reference_golden(golden):
+    """K5 / K8 against outputs of the reference's OWN utils/output.py functions (golden vectors)."""
+    from b200calib import output as O
+    lg = torch.from_numpy(golden["kp_logits"])
+    for th, tag in ((0.75, "75"), (0.999, "999")):
+        idx, cls, pr = O.get_key_point_predictions(lg, th)
+        assert np.array_equal(cls, golden["kp_cls" + tag]) and np.array_equal(idx, golden["kp_idx" + tag])
+        assert np.allclose(pr.numpy(), golden["kp_pr" + tag], atol=2e-6)
+    idx, cls, pr = O.get_key_point_predictions(torch.from_numpy(golden["kp10_logits"]), 0.75)
+    assert np.array_equal(cls, golden["kp10_cls"]) and np.array_equal(idx, golden["kp10_idx"])
+    vo = torch.from_numpy(golden["vote_out"])
+    assert np.allclose(O.get_pred_center(vo, golden["vote_coords"], ee_r=0.02), golden["vote_center"], atol=1e-6)
+    assert np.allclose(O.get_pred_center(vo, golden["vote_coords"], ee_r=0.02, q=golden["vote_q"]),
+                       golden["vote_center_q"], atol=1e-6)
+    # segmentation arg-max: the kernel the pipeline uses (K5 arg-max by-product) and the field-level helper
+    import MinkowskiEngine as ME
+    from MinkowskiEngine._lib import ptr, stream, check
+    sl = torch.from_numpy(golden["seg_logits"]).cuda().contiguous()
+    eye = torch.eye(3, device="cuda").contiguous()
+    am = torch.empty((sl.shape[0],), dtype=torch.uint8, device="cuda")
+    check(ME._C.b2me_linear_small(ptr(sl), 0, sl.shape[0], 3, ptr(eye), None, 3, None, ptr(am), stream()))
+    assert np.array_equal(am.cpu().numpy().astype(np.int64), golden["seg_preds"])
+
+    class _Field:
+        features = sl
+    preds, conf = O.get_segmentations_from_tensor_field(_Field())
+    assert np.array_equal(preds, golden["seg_preds"]) and np.allclose(conf, golden["seg_conf"], atol=1e-6)

@@ -95,3 +95,29 @@ def test_oracle_pipeline_small_frame(built_lib):
     assert r["segmentation"].shape == (len(f["points"]),) and set(np.unique(r["segmentation"])) <= {0, 1, 2}
     assert r["ee_pose"] is not None and r["ee_pose"].shape == (7,) and abs(np.linalg.norm(r["ee_pose"][3:]) - 1) < 1e-6
     assert r["key_points_pose"] is not None and r["icp_stats"][2] >= 1
+
+
+def test_heads_vs_reference_golden(golden):
+    """oracle restatements of utils/output.py:45-87 against outputs of the reference's own functions
+    (tests/golden/make_golden.py imports utils/output.py with the oracle package standing in for MinkowskiEngine)."""
+    for th, tag in ((0.75, "75"), (0.999, "999")):
+        idx, cls, pr = G.key_point_predictions(golden["kp_logits"], th)
+        assert np.array_equal(cls, golden["kp_cls" + tag]) and np.array_equal(idx, golden["kp_idx" + tag])
+        assert np.allclose(np.asarray(pr), golden["kp_pr" + tag], atol=1e-7)
+    idx, cls, pr = G.key_point_predictions(golden["kp10_logits"], 0.75)
+    assert np.array_equal(cls, golden["kp10_cls"]) and np.array_equal(idx, golden["kp10_idx"])
+    assert np.allclose(G.pred_center(golden["vote_out"], golden["vote_coords"], ee_r=0.02), golden["vote_center"],
+                       atol=1e-6)
+    assert np.allclose(G.pred_center(golden["vote_out"], golden["vote_coords"], ee_r=0.02, q=golden["vote_q"]),
+                       golden["vote_center_q"], atol=1e-6)
+    assert np.array_equal(G.segmentation_labels(golden["seg_logits"]), golden["seg_preds"])
+
+
+def test_pose_metric_vs_reference_golden(golden):
+    """the tolerance metric of the pose parity tests (rotation angle, translation distance) against
+    utils/metrics.py:110-127 compute_pose_metrics."""
+    for i, (p, p2) in enumerate(zip(golden["pose"], golden["pose2"])):
+        Ra = G.quaternion_rotation_matrix(p[3:], switch_w=False)
+        Rb = G.quaternion_rotation_matrix(p2[3:], switch_w=False)
+        assert abs(np.radians(G.rotation_angle_deg(Ra, Rb)) - golden["metric_angle"][i]) < 1e-6, i
+        assert abs(np.linalg.norm(p[:3] - p2[:3]) - golden["metric_dist"][i]) < 1e-12

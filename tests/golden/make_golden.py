@@ -125,6 +125,50 @@ def main():
                seg_logits=seg_logits.numpy(), seg_preds=seg_preds, seg_conf=seg_conf,
                metric_dist=np.array([m["dist_position"] for m in pm]),
                metric_angle=np.array([m["angle_diff"] for m in pm]))
+    # ---- "magic" translation: the reference's own InferenceEngine.predict_translation (app/inference_engine.py:459-489),
+    #      imported with stub modules for what is not installed (open3d, tensorboardX, openpyxl: none is touched by
+    #      this method) and the oracle package as MinkowskiEngine; utils/config.py parses sys.argv at import time
+    import tempfile
+    import types
+    tmp = tempfile.mkdtemp(prefix="b2me_golden_")
+    argv0 = sys.argv
+    sys.argv = ["x", "--config", os.path.join(REF, "config", "default.yaml"), "--log_path", os.path.join(tmp, "log.log"),
+                "--exp_path", os.path.join(tmp, "exp")]
+    for name in ("open3d", "tensorboardX", "openpyxl"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.SummaryWriter = object
+            sys.modules[name] = m
+    import oracle.MinkowskiEngine.modules.resnet_block as _rb
+    import oracle.MinkowskiEngine.utils as _mu
+    import oracle.MinkowskiEngine.MinkowskiOps as _mo
+    sys.modules["MinkowskiEngine.modules"] = OME.modules
+    sys.modules["MinkowskiEngine.modules.resnet_block"] = _rb
+    sys.modules["MinkowskiEngine.utils"] = _mu
+    sys.modules["MinkowskiEngine.MinkowskiOps"] = _mo
+    sys.path.insert(0, os.path.join(REF, "app"))
+    from app import inference_engine as IE
+    sys.argv = argv0
+    eng = object.__new__(IE.InferenceEngine)     # predict_translation only reads the module-level config
+    tr_pts, tr_q, tr_out, tr_n = [], [], [], []
+    nmax = 3000
+    for case in range(8):
+        n = int(rng.integers(600, nmax + 1))
+        qq = rng.normal(size=4)
+        qq /= np.linalg.norm(qq)
+        Rq = T.get_quaternion_rotation_matrix(qq, switch_w=False)
+        box = (rng.random((n, 3)) * np.array([0.10, 0.22, 0.126]) - np.array([0.0, 0.11, 0.0]))
+        pts = (box @ Rq.T + np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(1.0, 1.5)])
+               ).astype(np.float32)
+        pos, _ = eng.predict_translation(pts, None, qq.astype(np.float32))
+        pad = np.zeros((nmax, 3), np.float32)
+        pad[:n] = pts
+        tr_pts.append(pad); tr_q.append(qq.astype(np.float32)); tr_out.append(np.asarray(pos, dtype=np.float64))
+        tr_n.append(n)
+    out.update(trans_pts=np.array(tr_pts), trans_q=np.array(tr_q), trans_out=np.array(tr_out),
+               trans_n=np.array(tr_n, dtype=np.int32))
+    for k in [k for k in sys.modules if k.startswith("MinkowskiEngine")]:
+        sys.modules.pop(k)
     np.savez_compressed(os.path.join(HERE, "reference_geometry.npz"), **out)
 
     # ---- CAD input fixture: xyz of app/hand_files/hand.pcd (4480 points), read with our PCD reader

@@ -119,3 +119,17 @@ def test_heads_vs_reference_golden(golden):
         features = sl
     preds, conf = O.get_segmentations_from_tensor_field(_Field())
     assert np.array_equal(preds, golden["seg_preds"]) and np.allclose(conf, golden["seg_conf"], atol=1e-6)
+
+
+def test_translation_magic_vs_reference_golden(golden):
+    """fused translation kernel against InferenceEngine.predict_translation of the reference itself; tolerance
+    1e-4 m (north star), observed ~1e-6 (fp32 rotation like the reference, fp64 tail)."""
+    from b200calib import output as O
+    ns = golden["trans_n"]
+    offs = np.concatenate(([0], np.cumsum(ns))).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate([golden["trans_pts"][i][:n] for i, n in enumerate(ns)])).cuda()
+    out = O.translation_magic_batched(pts, offs, torch.from_numpy(golden["trans_q"]).cuda()).cpu().numpy()
+    err = np.abs(out - golden["trans_out"]).max()
+    print("translation max abs err vs reference", err)
+    assert err < 1e-4
+    assert err < 2e-5

@@ -121,3 +121,10 @@ def test_pose_metric_vs_reference_golden(golden):
         Rb = G.quaternion_rotation_matrix(p2[3:], switch_w=False)
         assert abs(np.radians(G.rotation_angle_deg(Ra, Rb)) - golden["metric_angle"][i]) < 1e-6, i
         assert abs(np.linalg.norm(p[:3] - p2[:3]) - golden["metric_dist"][i]) < 1e-12
+
+
+def test_translation_magic_vs_reference_golden(golden):
+    """a17b against InferenceEngine.predict_translation of the reference itself (app/inference_engine.py:459-489)."""
+    for i, n in enumerate(golden["trans_n"]):
+        got = G.translation_magic(golden["trans_pts"][i][:n], golden["trans_q"][i])
+        assert np.allclose(got, golden["trans_out"][i], atol=1e-6), (i, got, golden["trans_out"][i])

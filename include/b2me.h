@@ -242,6 +242,26 @@ int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz
                          double* out_T, double* out_stats, void* ws, size_t ws_bytes,
                          b2me_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PointNet++ primitives of the default key-point network (model/pointnet2.py:9-43 through
+ * model/pointnet2_utils.py). All clouds of a batch have N points.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* farthest_point_sample (model/pointnet2_utils.py:65-86): xyz [B,N,3] f32, start [B] i32 first sample of every cloud
+ * (the reference draws it with torch.randint; null = 0), out_idx [B,npoint] i32. N <= 8192. Ties: lowest index. */
+int b2me_fps(const float* xyz, int B, int N, int npoint, const int32_t* start, int32_t* out_idx,
+             b2me_stream_t stream);
+
+/* query_ball_point (model/pointnet2_utils.py:89-110): out_idx [B,S,nsample] i32 = the first nsample indices
+ * (ascending) with squared distance <= radius^2 to new_xyz [B,S,3], padded with the first; N when none. */
+int b2me_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, float radius, int nsample,
+                    int32_t* out_idx, b2me_stream_t stream);
+
+/* 3-NN of PointNetFeaturePropagation (model/pointnet2_utils.py:283-293): for every point of xyz1 [B,N,3] the three
+ * nearest points of xyz2 [B,S,3] (out_idx [B,N,3] i32) and the weights (1/(d+1e-8)) / sum (out_w [B,N,3] f32). */
+int b2me_three_nn(const float* xyz1, const float* xyz2, int B, int N, int S, int32_t* out_idx, float* out_w,
+                  b2me_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

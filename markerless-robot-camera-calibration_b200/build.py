@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb2me.so")
-SOURCES = ["api.cu", "coords.cu", "spconv_simt.cu", "spconv_tc.cu", "heads.cu", "cluster.cu", "pose.cu"]
+SOURCES = ["api.cu", "coords.cu", "spconv_simt.cu", "spconv_tc.cu", "heads.cu", "cluster.cu", "pose.cu", "pointnet.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DB2ME_BUILD",

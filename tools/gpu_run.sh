@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest17.log 2>&1; echo "all rc=$?"
-tail -5 gpurun_out/pytest17.log
+timeout 600 python -m pytest tests/test_gpu_pointnet2.py -x -q -m gpu -s > gpurun_out/pytest_pn2.log 2>&1; echo "rc=$?"
+tail -25 gpurun_out/pytest_pn2.log

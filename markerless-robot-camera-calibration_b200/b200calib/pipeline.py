@@ -336,14 +336,15 @@ class BatchedInferenceEngine:
         return bp, bi
 
     @torch.no_grad()
-    def predict_device(self, points, rgb, bidx, offs, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None):
+    def predict_device(self, points, rgb, bidx, offs, ee2base_poses=None, gt_labels=None, kp_conf_threshold=None,
+                       rgb_normalized=False):
         """the whole per-batch pipeline on tensors that are already resident on the device.
         points/rgb [N,3] f32, bidx [N] f32 frame index, offs [nb+1] host frame offsets; gt_labels: optional
         [N] uint8 device tensor used for the EE crop instead of the predicted labels (random-init weights give no
         usable EE). Returns (per-point labels uint8 on the device, pose dict on the host)."""
         nb = len(offs) - 1
         with _Stage(self, "segmentation"):
-            rgbn = normalize_colors_(rgb)
+            rgbn = rgb if rgb_normalized else normalize_colors_(rgb)   # b200calib.ingest already normalises
             labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
             del fld, out
         seg_labels = labels

@@ -562,3 +562,83 @@ extern "C" int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
+
+// ------------------------------------------------------------------------------------------ ingest
+// Organised PointCloud2 / PCD records (x, y, z f32 + PCL-packed rgb: 0x00RRGGBB in the bits of a float) of a batch
+// of frames -> the tensors K1 consumes, in one pass on the device instead of the reference's NumPy hops:
+//   utils/ros_utils.py:142-167  drop non-finite points, split the packed rgb
+//   app/freenect_data_engine.py:81  rgb / 255           utils/preprocess.py:20-37  rgb - 0.5
+//   utils/data.py:58-75  ROI mask (strict inequalities)
+// Order-preserving compaction (flags -> exclusive scan -> scatter), so first-occurrence voxel order is unchanged.
+__global__ void k_ingest_flags(const float4* __restrict__ rec, int64_t n, float min_x, float max_x, float min_y,
+                               float max_y, float min_z, float max_z, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r = rec[i];
+    const bool ok = isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && r.x > -500.f && r.x < max_x && r.x > min_x &&
+                    r.y < max_y && r.y > min_y && r.z < max_z && r.z > min_z;
+    flag[i] = ok ? 1 : 0;
+}
+
+__global__ void k_ingest_scatter(const float4* __restrict__ rec, int64_t n, const int32_t* __restrict__ pos,
+                                 const int32_t* __restrict__ total, const int32_t* __restrict__ frame_offsets, int F,
+                                 float* __restrict__ out_xyz, float* __restrict__ out_rgb, float* __restrict__ out_bidx,
+                                 int32_t* __restrict__ out_src, int32_t* __restrict__ out_offsets) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= F) {  // compacted frame offsets: position of the frame's first input record
+        const int32_t fo = frame_offsets[i];
+        out_offsets[i] = fo < n ? pos[fo] : *total;
+    }
+    if (i >= n) return;
+    const int32_t p = pos[i];
+    const int32_t nxt = (i + 1 < n) ? pos[i + 1] : *total;
+    if (nxt == p) return;  // dropped
+    const float4 r = rec[i];
+    int lo = 0, hi = F;    // frame of record i: largest f with frame_offsets[f] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (frame_offsets[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    out_xyz[(int64_t)p * 3 + 0] = r.x;
+    out_xyz[(int64_t)p * 3 + 1] = r.y;
+    out_xyz[(int64_t)p * 3 + 2] = r.z;
+    const unsigned int c = __float_as_uint(r.w);
+    out_rgb[(int64_t)p * 3 + 0] = (float)((double)((c >> 16) & 255u) / 255.0 - 0.5);
+    out_rgb[(int64_t)p * 3 + 1] = (float)((double)((c >> 8) & 255u) / 255.0 - 0.5);
+    out_rgb[(int64_t)p * 3 + 2] = (float)((double)(c & 255u) / 255.0 - 0.5);
+    out_bidx[p] = (float)lo;
+    if (out_src) out_src[p] = (int32_t)i;
+}
+
+extern "C" size_t b2me_ingest_workspace_bytes(int64_t n) {
+    const int64_t n1 = n > 0 ? n : 1;
+    return align_up((size_t)(n1 + 1) * 4, 256) + align_up(16, 256) + scan_ws_bytes(n1 + 1);
+}
+
+extern "C" int b2me_ingest_clouds(const float* xyzrgb, int64_t n, const int32_t* frame_offsets, int F,
+                                  const float* roi6, float* out_xyz, float* out_rgb, float* out_bidx, int32_t* out_src,
+                                  int32_t* out_offsets, void* ws, size_t ws_bytes, b2me_stream_t stream) {
+    if (!xyzrgb || !frame_offsets || !out_xyz || !out_rgb || !out_bidx || !out_offsets || !ws || n < 0 || F < 1)
+        return B2ME_EINVAL;
+    if (n >= (int64_t)1 << 31) return B2ME_EINVAL;
+    if (ws_bytes < b2me_ingest_workspace_bytes(n)) return B2ME_EWORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    char* base = reinterpret_cast<char*>(ws);
+    int32_t* pos = reinterpret_cast<int32_t*>(base);
+    int32_t* total = reinterpret_cast<int32_t*>(base + align_up((size_t)(n + 1) * 4, 256));
+    void* scan = base + align_up((size_t)(n + 1) * 4, 256) + align_up(16, 256);
+    float r[6] = {-500.f, 500.f, -500.f, 500.f, -500.f, 500.f};  // utils/data.py:58 defaults
+    if (roi6)
+        for (int i = 0; i < 6; ++i) r[i] = roi6[i];  // host array
+    const unsigned G = (unsigned)ceil_div64((n > F ? n : F) + 1, 256);
+    if (n > 0) k_ingest_flags<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(xyzrgb), n,
+                                                                              r[0], r[1], r[2], r[3], r[4], r[5], pos);
+    cudaMemsetAsync(pos + n, 0, 4, s);
+    const int rc = exclusive_scan_i32(pos, n + 1, total, scan, s);
+    if (rc != B2ME_OK) return rc;
+    k_ingest_scatter<<<G, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzrgb), n, pos, total, frame_offsets, F, out_xyz,
+                                       out_rgb, out_bidx, out_src, out_offsets);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

@@ -173,3 +173,28 @@ def icp_point_to_point(source, target, init_T, max_corr=0.1, max_iter=30, rel_fi
         if done:
             break
     return T, fit, rmse, it
+
+
+# ---- ingest (utils/ros_utils.py:142-167, app/freenect_data_engine.py:81, utils/preprocess.py:20-37, utils/data.py:58-75)
+def roi_mask(points, min_x=-500, max_x=500, min_y=-500, max_y=500, min_z=-500, max_z=500, offset=0.0):
+    """utils/data.py:58-75: strict box test (and x > -500)."""
+    p = np.asarray(points)
+    # the reference compares the (float32) array with Python scalars: the comparison runs in the array's dtype
+    lo = (np.array([min_x, min_y, min_z], dtype=np.float64) - offset).astype(p.dtype)
+    hi = (np.array([max_x, max_y, max_z], dtype=np.float64) + offset).astype(p.dtype)
+    return (p[:, 0] > -500) & np.all(p < hi, axis=1) & np.all(p > lo, axis=1)
+
+
+def ingest_records(rec, roi=None):
+    """[n,4] f32 records (x, y, z, PCL-packed rgb) of ONE frame -> (points f32 [n',3], rgb f32 [n',3] in
+    [-0.5, 0.5], kept input indices): non-finite points dropped, rgb split, / 255, - 0.5, ROI mask."""
+    rec = np.asarray(rec, dtype=np.float32)
+    ok = np.isfinite(rec[:, 0]) & np.isfinite(rec[:, 1]) & np.isfinite(rec[:, 2])
+    bits = rec[:, 3].copy().view(np.uint32)
+    rgb = np.stack(((bits >> 16) & 255, (bits >> 8) & 255, bits & 255), axis=1).astype(np.float64)
+    pts = rec[:, :3]
+    with np.errstate(invalid="ignore"):
+        ok &= roi_mask(pts, *(roi if roi is not None else ()))
+    rgbn = (rgb / 255.0 - 0.5).astype(np.float32)
+    keep = np.nonzero(ok)[0]
+    return pts[keep], rgbn[keep], keep

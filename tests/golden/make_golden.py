@@ -125,6 +125,16 @@ def main():
                seg_logits=seg_logits.numpy(), seg_preds=seg_preds, seg_conf=seg_conf,
                metric_dist=np.array([m["dist_position"] for m in pm]),
                metric_angle=np.array([m["angle_diff"] for m in pm]))
+    # ---- ROI mask (utils/data.py:58-75), reference's own function
+    from utils import data as RD
+    roi_pts = rng.normal(0, 1.0, (4000, 3)).astype(np.float32)
+    roi_pts[::97] = 0.75          # points exactly on a limit: strict inequalities drop them
+    roi_args = dict(min_x=-0.8, max_x=0.75, min_y=-1.2, max_y=0.9, min_z=-0.75, max_z=2.0)
+    out.update(roi_pts=roi_pts, roi_limits=np.array([roi_args[k] for k in ("min_x", "max_x", "min_y", "max_y", "min_z",
+                                                                             "max_z")], dtype=np.float64),
+               roi_mask=RD.get_roi_mask(roi_pts, **roi_args), roi_mask_default=RD.get_roi_mask(roi_pts),
+               roi_mask_offset=RD.get_roi_mask(roi_pts, offset=0.1, **roi_args))
+
     # ---- "magic" translation: the reference's own InferenceEngine.predict_translation (app/inference_engine.py:459-489),
     #      imported with stub modules for what is not installed (open3d, tensorboardX, openpyxl: none is touched by
     #      this method) and the oracle package as MinkowskiEngine; utils/config.py parses sys.argv at import time

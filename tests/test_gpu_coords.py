@@ -133,3 +133,38 @@ def test_full_size_properties():
     assert torch.allclose(st.F.double(), mean, atol=1e-6)
     st2 = ME.TensorField(features=fld.F, coordinates=co, device="cuda").sparse()      # idempotent / deterministic
     assert torch.equal(st2.C, C) and torch.equal(st2.F, st.F)
+
+
+def test_ingest_clouds_matches_oracle_and_reference_roi(golden):
+    """fused on-device ingest of PointCloud2-style records against the NumPy restatement of the
+    reference's host path, and its ROI test against the reference's own get_roi_mask outputs (golden)."""
+    from b200calib.ingest import ingest_clouds, pack_xyzrgb
+    from oracle import geometry as G
+    rng = np.random.default_rng(9)
+    frames, recs = [], []
+    for f in range(4):
+        n = int(rng.integers(1, 5000)) if f != 2 else 0            # frame 2 is empty
+        pts = rng.normal(0, 1.0, (n, 3)).astype(np.float32)
+        if n:
+            pts[rng.random(n) < 0.05] = np.nan                      # invalid depth pixels
+            pts[rng.random(n) < 0.01, 1] = np.inf
+        rec = pack_xyzrgb(pts, rng.integers(0, 256, (n, 3)))
+        frames.append(rec)
+    offs = np.concatenate(([0], np.cumsum([len(r) for r in frames]))).astype(np.int32)
+    allrec = torch.from_numpy(np.concatenate(frames)).cuda()
+    roi = (-0.8, 0.75, -1.2, 0.9, -0.75, 2.0)
+    for r in (None, roi):
+        pts, rgb, bidx, noffs, src = ingest_clouds(allrec, offs, roi=r, want_source_index=True)
+        for f, rec in enumerate(frames):
+            op, oc, keep = G.ingest_records(rec, r)
+            a, b = int(noffs[f]), int(noffs[f + 1])
+            assert b - a == len(op), (f, b - a, len(op))
+            assert np.array_equal(pts[a:b].cpu().numpy(), op)
+            assert np.array_equal(rgb[a:b].cpu().numpy(), oc), "colour normalisation must be bit-exact"
+            assert np.array_equal(src[a:b].cpu().numpy(), keep + offs[f])
+            assert np.all(bidx[a:b].cpu().numpy() == f)
+    # the ROI test itself against the reference's own function
+    rec = pack_xyzrgb(golden["roi_pts"], np.zeros((len(golden["roi_pts"]), 3)))
+    _, _, _, _, src = ingest_clouds(torch.from_numpy(rec).cuda(), [0, len(rec)], roi=tuple(golden["roi_limits"]),
+                                    want_source_index=True)
+    assert np.array_equal(src.cpu().numpy(), np.nonzero(golden["roi_mask"])[0])

@@ -128,3 +128,11 @@ def test_translation_magic_vs_reference_golden(golden):
     for i, n in enumerate(golden["trans_n"]):
         got = G.translation_magic(golden["trans_pts"][i][:n], golden["trans_q"][i])
         assert np.allclose(got, golden["trans_out"][i], atol=1e-6), (i, got, golden["trans_out"][i])
+
+
+def test_roi_mask_vs_reference_golden(golden):
+    lim = golden["roi_limits"]
+    assert np.array_equal(G.roi_mask(golden["roi_pts"], *lim), golden["roi_mask"])
+    assert np.array_equal(G.roi_mask(golden["roi_pts"]), golden["roi_mask_default"])
+    assert np.array_equal(G.roi_mask(golden["roi_pts"], *lim, offset=0.1), golden["roi_mask_offset"])
+    assert 0.2 < golden["roi_mask"].mean() < 0.8

@@ -177,6 +177,45 @@ def main():
         tr_n.append(n)
     out.update(trans_pts=np.array(tr_pts), trans_q=np.array(tr_q), trans_out=np.array(tr_out),
                trans_n=np.array(tr_n, dtype=np.int32))
+    # ---- calibration tail: the reference's own InferenceEngine.calibrate (app/inference_engine.py:152-244) on seeded
+    #      per-frame results of 3 robot positions (some frames unconfident, some without a key-point pose)
+    from dto import ResultDTO
+    eng.camera_link_transformation_pose = np.array([0.0, -0.045, 0.0, 0.5, -0.5, 0.5, 0.5], dtype=np.float32)
+    cal_rows = []
+    data = {}
+    true_base = poses[5].copy()
+    for pos_id in range(3):
+        lst = []
+        for fr in range(6):
+            def noisy(p, s):
+                o = p.copy()
+                o[:3] += rng.normal(0, s, 3)
+                o[3:] += rng.normal(0, s, 4)
+                o[3:] /= np.linalg.norm(o[3:])
+                return o
+            ee = noisy(poses[pos_id], 0.01)
+            conf = not (fr == 1 and pos_id == 0)
+            has_kp = not (fr == 2)
+            d = ResultDTO(segmentation=None, ee_pose=ee, base_pose=noisy(true_base, 0.01),
+                          key_points_pose=noisy(poses[pos_id], 0.01) if has_kp else None,
+                          key_points_base_pose=noisy(true_base, 0.01) if has_kp else None, is_confident=conf)
+            lst.append(d)
+            nanp = np.full(7, np.nan)
+            cal_rows.append(np.concatenate(([pos_id, float(conf)], d.ee_pose, d.base_pose,
+                                            d.key_points_pose if has_kp else nanp,
+                                            d.key_points_base_pose if has_kp else nanp)))
+        data[str(pos_id)] = lst
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        cal_all = eng.calibrate(data)
+        cal_one = eng.calibrate({"0": data["0"]})
+    out.update(calib_rows=np.array(cal_rows), calib_camera_link=eng.camera_link_transformation_pose,
+               calib_pose=np.asarray(cal_all.pose_camera_link), calib_base=np.asarray(cal_all.base_pose),
+               calib_kp_base=np.asarray(cal_all.key_points_base_pose),
+               calib_base_cl=np.asarray(cal_all.base_pose_camera_link),
+               calib_one_pose=np.asarray(cal_one.pose_camera_link),
+               calib_one_base_cl=np.asarray(cal_one.base_pose_camera_link))
     for k in [k for k in sys.modules if k.startswith("MinkowskiEngine")]:
         sys.modules.pop(k)
     np.savez_compressed(os.path.join(HERE, "reference_geometry.npz"), **out)

@@ -136,3 +136,31 @@ def test_roi_mask_vs_reference_golden(golden):
     assert np.array_equal(G.roi_mask(golden["roi_pts"]), golden["roi_mask_default"])
     assert np.array_equal(G.roi_mask(golden["roi_pts"], *lim, offset=0.1), golden["roi_mask_offset"])
     assert 0.2 < golden["roi_mask"].mean() < 0.8
+
+
+def test_calibrate_vs_reference_golden(golden, built_lib):
+    """the calibration tail (b200calib.calibration.calibrate) against InferenceEngine.calibrate of the reference
+    itself (app/inference_engine.py:152-244): several positions, unconfident frames, frames without key points."""
+    from b200calib import calibration as C
+    from b200calib.pipeline import FrameResult
+    rows = golden["calib_rows"]
+    data = {}
+    for r in rows:
+        kp = None if np.isnan(r[16]) else r[16:23]
+        kpb = None if np.isnan(r[23]) else r[23:30]
+        fr = FrameResult(segmentation=None, ee_pose=r[2:9], base_pose=r[9:16], key_points_pose=kp,
+                         key_points_base_pose=kpb, is_confident=bool(r[1]))
+        data.setdefault(str(int(r[0])), []).append(fr)
+    cl = golden["calib_camera_link"]
+
+    def close(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return np.allclose(a[:3], b[:3], atol=1e-9) and min(np.abs(a[3:] - b[3:]).max(), np.abs(a[3:] + b[3:]).max()) < 1e-9
+    allr = C.calibrate(data, camera_link_transformation_pose=cl)
+    assert close(allr.pose_camera_link, golden["calib_pose"]) and close(allr.base_pose, golden["calib_base"])
+    assert close(allr.key_points_base_pose, golden["calib_kp_base"])
+    assert close(allr.base_pose_camera_link, golden["calib_base_cl"])
+    one = C.calibrate({"0": data["0"]}, camera_link_transformation_pose=cl)
+    assert close(one.pose_camera_link, golden["calib_one_pose"])
+    assert close(one.base_pose_camera_link, golden["calib_one_base_cl"])
+    assert C.calibrate({"0": data["0"][:1]}) is None   # fewer than 2 confident frames

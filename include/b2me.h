@@ -154,7 +154,9 @@ int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, vo
  * every convolution on that kernel map. */
 int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, int K, uint32_t* masks,
                        b2me_stream_t stream);
-int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2,
+/* V_in: rows of in1 (and of in2, which lies on the same coordinate map); the gathered rows are fetched through TMA
+ * tensor maps built per call (tile::gather4: row indices outside [0, V_in) read as zeros). */
+int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in,
                        const void* packed_w, const int32_t* nbr, const int32_t* perm,
                        const uint32_t* tile_masks, int K,
                        int64_t V_out, int Cout, const float* scale, const float* shift,

@@ -35,7 +35,7 @@ SIGNATURES = {
     "b2me_tc_supported": (_i32, [_i32, _i32, _i32, _i32]),
     "b2me_tc_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2me_tc_tile_masks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
-    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
+    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
                                   _f32, _vp, _i32, _vp]),
     "b2me_affine_act": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "b2me_convert": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp]),

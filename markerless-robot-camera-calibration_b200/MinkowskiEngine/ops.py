@@ -130,7 +130,7 @@ def _run_conv(p):
         out = torch.empty((V_out, Cout), dtype=torch.bfloat16, device=dev)
         perm, masks = p.perm() if p.perm is not None else (None, None)
         ev = _profile_conv("tc", p, Cin1 + Cin2)
-        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, ptr(packed), ptr(p.nbr), ptr(perm), ptr(masks), K,
+        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, f1.shape[0], ptr(packed), ptr(p.nbr), ptr(perm), ptr(masks), K,
                                      V_out, Cout, ptr(p.scale), ptr(p.shift), ptr(res), p.act, p.slope, ptr(out),
                                      _lib.BF16, stream()), "spconv_fwd_tc")
         if ev is not None:

@@ -33,6 +33,7 @@
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
 #include <stdlib.h>
 
 #define TC_BM 128
@@ -81,6 +82,13 @@ struct TcParams {
     unsigned int b_bytes;
     int total_work;  // 256-row tile pairs x n-tiles
     int debug;       // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
+    int tma;         // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
+    // tensor maps (TMA mode): the two sources as [V_in, Cin] bf16 with a 64-channel x 1-row box (SWIZZLE_128B; rows are
+    // picked by tile::gather4, absent neighbours (-1) and channels past Cin are out of bounds = zero-filled) and the
+    // packed weights as 128-byte rows (box = one CTA's half of an item, no swizzle: the image is pre-swizzled)
+    alignas(64) CUtensorMap tm_in1;
+    alignas(64) CUtensorMap tm_in2;
+    alignas(64) CUtensorMap tm_w;
 };
 
 // Optional in-kernel role timers (build with -DB2ME_TC_PROFILE; tools/conv_probe.py): cycles that lane 0 of each
@@ -175,6 +183,30 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// TMA loads of a CTA pair (cta_group::2): the data lands in the issuing CTA's shared memory, the complete_tx goes to
+// the mbarrier at cluster address `bar_cluster` (the LEADER's stage barrier, in either CTA), so the MMA thread waits on
+// one barrier for both CTAs' operands and no relay is needed.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst, const CUtensorMap* tm, int col, int r0, int r1, int r2,
+                                                 int r3, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int col, int row,
+                                                 uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(bar_cluster)
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -284,6 +316,83 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t a_des
             : "memory");
     }
 }
+// one lane of the (converged) warp: true in exactly one lane
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+// tcgen05.mma with descriptors given as low words (see below), executed by the calling thread
+__device__ __forceinline__ void tc_mma_lo(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+}
+// Warp-uniform issue helpers: ALL lanes execute the statement with identical operands, elect.sync picks the issuing
+// lane inside the block. Descriptors are passed as their low words (start address >> 4 | LBO field); the high word of
+// the SWIZZLE_128B K-major descriptor (SBO 1024 B, version 1, swizzle mode 2) is the constant 0x40004040.
+// FENCE: the elected lane first orders the generic-proxy (cp.async) writes of the stage before its async-proxy reads.
+template <bool FENCE>
+__device__ __forceinline__ void tc_kstep2(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b0_lo, uint32_t b1_lo,
+                                          uint32_t idesc0, uint32_t idesc1, uint32_t accumulate) {
+    if (FENCE) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0, db1;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %7, 0;\n\t"
+            "mov.b64 da, {%2, %8};\n\tmov.b64 db0, {%3, %8};\n\tmov.b64 db1, {%4, %8};\n\t"
+            "@q fence.proxy.async.shared::cta;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %5, p;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da, db1, %6, p;\n\t}" ::"r"(d0),
+            "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(idesc0), "r"(idesc1), "r"(accumulate), "r"(0x40004040u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0, db1;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %7, 0;\n\t"
+            "mov.b64 da, {%2, %8};\n\tmov.b64 db0, {%3, %8};\n\tmov.b64 db1, {%4, %8};\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %5, p;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da, db1, %6, p;\n\t}" ::"r"(d0),
+            "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(idesc0), "r"(idesc1), "r"(accumulate), "r"(0x40004040u)
+            : "memory");
+    }
+}
+template <bool FENCE>
+__device__ __forceinline__ void tc_kstep1(uint32_t d0, uint32_t a_lo, uint32_t b0_lo, uint32_t idesc0,
+                                          uint32_t accumulate) {
+    if (FENCE) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db0, {%2, %5};\n\t"
+            "@q fence.proxy.async.shared::cta;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %3, p;\n\t}" ::"r"(d0),
+            "r"(a_lo), "r"(b0_lo), "r"(idesc0), "r"(accumulate), "r"(0x40004040u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db0, {%2, %5};\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %3, p;\n\t}" ::"r"(d0),
+            "r"(a_lo), "r"(b0_lo), "r"(idesc0), "r"(accumulate), "r"(0x40004040u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_commit_pair_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
@@ -301,7 +410,7 @@ __host__ __device__ __forceinline__ int tc_n_first(int n_tile) { return n_tile >
 
 // KT = kernel volume of the map (27: k3 s1, 8: k2 s2 and its transpose, 1: identity / MinkowskiLinear)
 template <int KT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -310,7 +419,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     const int S = p.stages;
     const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    // shfl-broadcast: the compiler then knows the warp index (hence every role branch) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
     // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 8 x 2 KB][barriers][tmem ptr]
@@ -343,7 +453,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             // 128 producer threads (cp.async-completion arrivals) + the B expect_tx arrive (+ the peer's relay)
-            mbar_init(bar_full + 8 * s, rank == 0 ? 130 : 129);
+            // TMA mode: the leader's single arrive.expect_tx (all four transfers complete_tx on the leader's barrier)
+            mbar_init(bar_full + 8 * s, p.tma ? 1 : (rank == 0 ? 130 : 129));
             mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit (multicast from the leader)
         }
         mbar_init(bar_nbr_full, 2);            // 2 prefetch warps
@@ -380,7 +491,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         return m ? m : 1u;
     };
 
-    if (warp < 4) {
+    if (warp < 4 && p.tma) {
+        // =============================== gather producers, TMA mode ===============================
+        // warp w owns rows 32 w .. 32 w + 31 of the CTA's tile: lanes 0-7 each issue ONE tile::gather4 per item (4
+        // rows x 128 bytes straight into the swizzled image; absent neighbours = row -1 = out of bounds = zeros), lanes
+        // 8-31 prefetch the next offset's rows into L2. Four warps = four schedulers issue the 32 UTMALDG of an item.
+        const uint32_t full_leader = mapa_u32(bar_full, 0u);
+        const int r0 = 32 * warp + 4 * lane;        // lanes 0-7: first of this lane's 4 rows
+        const int tp = 24 * warp + lane - 8;        // lanes 8-31: prefetch thread id 0..95
+        int ist = 0, iph = 0, it = 0;
+        uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+        for (int w = unit0; w < p.total_work; w += G, ++it) {
+            const uint32_t kmask = kmask_next;
+            if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+            mbar_wait(bar_nbr_full, (uint32_t)it & 1u);
+#pragma unroll 1
+            for (int k = 0; k < KT; ++k) {
+                if (!((kmask >> k) & 1u)) continue;
+                int id0 = -1, id1 = -1, id2 = -1, id3 = -1;
+                if (lane < 8) {
+                    id0 = nbr_s[(r0 + 0) * KT + k];
+                    id1 = nbr_s[(r0 + 1) * KT + k];
+                    id2 = nbr_s[(r0 + 2) * KT + k];
+                    id3 = nbr_s[(r0 + 3) * KT + k];
+                }
+                if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_nbr_empty);
+                } else if (TC_L2_PREFETCH && lane >= 8) {
+                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
+                    for (int L = tp; L < TC_BM * nchunk; L += 96) {
+                        const int r = L / nchunk, ch = L - r * nchunk;
+                        const int id = nbr_s[r * KT + k2];
+                        if (id >= 0) {
+                            if (ch < p.nchunk1) prefetch_l2(p.in1 + (long long)id * p.Cin1 + ch * TC_BK);
+                            else prefetch_l2(p.in2 + (long long)id * p.Cin2 + (ch - p.nchunk1) * TC_BK);
+                        }
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u);
+                    if (lane < 8) {
+                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes + (uint32_t)r0 * 128u;
+                        if (c < p.nchunk1)
+                            tma_gather4_pair(a_s, &p.tm_in1, c * TC_BK, id0, id1, id2, id3, full_leader + 8 * ist);
+                        else
+                            tma_gather4_pair(a_s, &p.tm_in2, (c - p.nchunk1) * TC_BK, id0, id1, id2, id3,
+                                             full_leader + 8 * ist);
+                    }
+                    if (++ist == S) { ist = 0; iph ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 4) {
         // =============================== gather producers ===============================
         const int j = tid & 7;        // 16-byte piece inside the 128-byte row
         const int rbase = tid >> 3;   // rows rbase + 16*i
@@ -461,91 +625,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // The whole warp walks the item list and waits on the barriers; lane 0 alone issues the tcgen05 instructions
         // (measured: a wait executed by a lone lane of a divergent warp costs ~210 cycles even on a complete phase).
         if (rank == 0) {
+            // The whole warp walks the item list with warp-uniform values; every tcgen05 instruction sits in an asm
+            // block that elects the issuing lane itself (elect.sync), so the compiler emits ELECT + predicated
+            // UTCHMMA instead of a per-lane serialisation loop: ~90 instead of ~300 SASS instructions per item. The
+            // tensor pipe queues only a couple of MMAs, so every cycle of issue overhead beyond that slack idles it.
             const int n_a = tc_n_first(p.n_tile), n_b = p.n_tile - n_a;  // N of the one or two MMAs per K step
             // kind::f16, bf16 x bf16 -> f32, K-major A and B, M = 256 (cta_group::2); each CTA's smem holds N/2 rows
             const uint32_t idesc_a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_a >> 3) << 17) | (16u << 24);
             const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_b >> 3) << 17) | (16u << 24);
+            // K steps (16 channels) of a full chunk and of the last chunk of each source
+            const int ks_last1 = (p.Cin1 - (p.nchunk1 - 1) * TC_BK) / 16;
+            const int ks_last2 = p.nchunk2 ? (p.Cin2 - (p.nchunk2 - 1) * TC_BK) / 16 : 0;
+            // low words of the SWIZZLE_128B K-major descriptors of stage 0 (high word is constant, see tc_kstep)
+            const uint32_t a_lo0 = ((base >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t stage_lo = stage_bytes >> 4;
+            const uint32_t b_off_lo = TC_A_BYTES >> 4, b2_off_lo = (TC_A_BYTES + (uint32_t)(n_a >> 1) * 128u) >> 4;
+            const bool need_fence = !p.tma;  // cp.async (generic proxy) writes of A -> visible to the MMA (async proxy)
             int st = 0, ph = 0, it = 0;
             PROF_DECL
             const long long t_role0 = clock64();
             (void)t_role0;
-            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+            // shfl-broadcast values are warp-uniform to the compiler: with the tile masks and the TMEM base uniform, the
+            // whole loop (stage index, phase, descriptors) is computed on the uniform datapath
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.total_work ? tile_mask(unit0) : 0u, 0);
             for (int w = unit0; w < p.total_work; w += G, ++it) {
                 const uint32_t kmask = kmask_next;
-                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+                if (w + G < p.total_work) kmask_next = __shfl_sync(0xffffffffu, tile_mask(w + G), 0);
                 // accumulator buffer of this work item and how often it has been used before
                 const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
                 const int au = p.acc_bufs == 2 ? (it >> 1) : it;
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * p.n_tile);
+                const uint32_t tmem_acc = tmem_u + (uint32_t)(ab * p.n_tile);
                 if (au > 0) {  // both CTAs' epilogues must have drained the previous tile of this buffer
                     PROF(2, mbar_wait(bar_tmem_empty + 8 * ab, (uint32_t)(au - 1) & 1u));
                     tc_fence_after();
                 }
                 uint32_t acc = 0u;
-                int sub = 0;
-                for (int k = 0; k < KT; ++k) {
-                    if (!((kmask >> k) & 1u)) continue;
+                for (uint32_t m = kmask; m; m &= m - 1u) {  // one pass per kernel offset the tile needs
                     for (int c = 0; c < nchunk; ++c) {
-                        const int kw = (c < p.nchunk1) ? min(TC_BK, p.Cin1 - c * TC_BK)
-                                                       : min(TC_BK, p.Cin2 - (c - p.nchunk1) * TC_BK);
-                        if (sub == 0) {
-                            PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
-                            PROF_COUNT(7);
-                        }
+                        int ks = (c == p.nchunk1 - 1) ? ks_last1 : ((c == nchunk - 1) ? ks_last2 : TC_BK / 16);
+#ifdef B2ME_TC_PROFILE
+                        if (p.debug & 4) ks = 0;
+#endif
+                        PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
+                        PROF_COUNT(7);
 #ifdef B2ME_TC_PROFILE
                         pt_ = clock64();
 #endif
-                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
-                        const bool group_last = (sub + 1 == TC_GI) || tile_last;
-                        if (lane == 0) {
-                            if (sub == 0) {
-                                fence_proxy_async();  // cp.async (generic proxy) writes of A -> visible to the MMA
-                                tc_fence_after();
-                            }
-                            const uint32_t a_s = base + (uint32_t)(st * TC_GI + sub) * stage_bytes;
-                            const uint32_t b_s = a_s + TC_A_BYTES;
-                            const uint64_t adesc = make_smem_desc_sw128(a_s);
-                            const uint64_t bdesc_a = make_smem_desc_sw128(b_s);
-                            const uint64_t bdesc_b = make_smem_desc_sw128(b_s + (uint32_t)(n_a >> 1) * 128u);
-                            for (int kk = 0; kk < ((p.debug & 4) ? 0 : kw / 16); ++kk) {
-                                if (n_b) {
-                                    // the two instructions share the A slice. Keeping it in the collector buffer
-                                    // (collector::a::fill / lastuse) was measured SLOWER on the K27 layers (863 ->
-                                    // 829 TFLOP/s), so both read A from shared memory (TC_A_COLLECTOR 0).
-                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 1 : 0>(tmem_acc, adesc + (uint64_t)(kk * 2),
-                                                                             bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
-                                    tc_mma_bf16_pair<TC_A_COLLECTOR ? 2 : 0>(tmem_acc + (uint32_t)n_a,
-                                                                             adesc + (uint64_t)(kk * 2),
-                                                                             bdesc_b + (uint64_t)(kk * 2), idesc_b, acc);
-                                } else {
-                                    tc_mma_bf16_pair<0>(tmem_acc, adesc + (uint64_t)(kk * 2),
-                                                        bdesc_a + (uint64_t)(kk * 2), idesc_a, acc);
-                                }
+                        tc_fence_after();
+                        const uint32_t a_lo = a_lo0 + (uint32_t)st * stage_lo;
+                        if (tc_elect_one()) {
+                            if (need_fence) fence_proxy_async();
+                            // the two instructions of a K step share the A slice; both read it from shared memory
+                            // (keeping it in the collector buffer, collector::a::fill / lastuse, was measured slower)
+                            for (int kk = 0; kk < ks; ++kk) {
+                                tc_mma_lo(tmem_acc, a_lo + 2u * kk, a_lo + b_off_lo + 2u * kk, idesc_a, acc);
+                                if (n_b)
+                                    tc_mma_lo(tmem_acc + (uint32_t)n_a, a_lo + 2u * kk, a_lo + b2_off_lo + 2u * kk,
+                                              idesc_b, acc);
                                 acc = 1u;
                             }
-                            if (group_last) tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
+                            tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
                         }
-                        if (group_last) {
-                            __syncwarp();
-                            sub = 0;
-                            if (++st == S) { st = 0; ph ^= 1; }
-                        } else {
-                            ++sub;
-                        }
+                        acc = ks > 0 ? 1u : acc;
+                        __syncwarp();
+                        if (++st == S) { st = 0; ph ^= 1; }
 #ifdef B2ME_TC_PROFILE
                         prof_[5] += (unsigned long long)(clock64() - pt_);
 #endif
                     }
                 }
-                if (lane == 0) tc_commit_pair(bar_tmem_full + 8 * ab);  // accumulators of both CTAs are complete
-                __syncwarp();
+                tc_commit_pair_elect(bar_tmem_full + 8 * ab);  // accumulators of both CTAs are complete
             }
 #ifdef B2ME_TC_PROFILE
             prof_[0] = (unsigned long long)(clock64() - t_role0);
             PROF_DUMP(1);
 #endif
-        } else {
+        } else if (!p.tma) {
             // peer: when a stage of THIS CTA is full (A gathered, B landed), tell the leader's full barrier
+            // (TMA mode: the peer's transfers complete_tx on the leader's barrier themselves, nothing to relay)
             int st = 0, ph = 0;
             PROF_DECL
             const long long t_role0 = clock64();
@@ -581,6 +739,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // =============================== weight (B) loader ===============================
         {
             int st = 0, ph = 0;
+            const uint32_t full_leader = mapa_u32(bar_full, 0u);
             uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
             for (int w = unit0; w < p.total_work; w += G) {
                 const uint32_t kmask = kmask_next;
@@ -596,7 +755,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             const uint32_t b_s = base + (uint32_t)(st * TC_GI + sub) * stage_bytes + TC_A_BYTES;
                             const uint8_t* g =
                                 p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
-                            if (p.debug & 2) {
+                            if (p.tma) {
+                                // leader: one arrive announcing all four transfers of the stage (A and B of both CTAs)
+                                if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * st, 2u * (TC_A_BYTES + p.b_bytes));
+                                const long long item = ((long long)nt * KT + k) * nchunk + c;
+                                tma_load_2d_pair(b_s, &p.tm_w, 0, (int)((item * 2 + rank) * (p.n_tile / 2)),
+                                                 full_leader + 8 * st);
+                            } else if (p.debug & 2) {
                                 if (sub == 0) mbar_arrive(bar_full + 8 * st);
                             } else {
                                 // one arrive per group, announcing the bytes of all its items (1 or TC_GI)
@@ -1054,6 +1219,39 @@ static int tc_num_sms() {
     return sms;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tc_encode_fn tc_encoder() {
+    static tc_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tc_encode_fn>(sym);
+    }
+    return fn;
+}
+// 2-D bf16 tensor [rows, cols] (row pitch = cols), box = box_cols x box_rows
+static bool tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                        uint32_t box_rows, CUtensorMapSwizzle swz) {
+    tc_encode_fn enc = tc_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || (cols * 2) % 16) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    return true;
+}
+
 template <int KT>
 static int tc_launch(const TcParams& p, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
@@ -1069,12 +1267,13 @@ static int tc_launch(const TcParams& p, size_t smem, cudaStream_t stream) {
     return B2ME_OK;
 }
 
-extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, const void* packed_w,
+extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in,
+                                  const void* packed_w,
                                   const int32_t* nbr, const int32_t* perm, const uint32_t* tile_masks, int K,
                                   int64_t V_out, int Cout,
                                   const float* scale, const float* shift, const void* residual, int act, float slope,
                                   void* out, int out_dtype, b2me_stream_t stream) {
-    if (!in1 || !packed_w || !out || V_out < 0) return B2ME_EINVAL;
+    if (!in1 || !packed_w || !out || V_out < 0 || V_in < 0) return B2ME_EINVAL;
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
     if (nbr && !tile_masks) return B2ME_EINVAL;
@@ -1128,6 +1327,26 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     }
 #endif
     p.stages = S;
+    // B2ME_TC_TMA=1 routes the operands through the TMA unit (tile::gather4 rows + 2-D weight boxes completing on the
+    // leader's barrier, no relay, no proxy fence). Measured on the same box it is slower than the default cp.async
+    // gather + bulk copy + relay path (K27 384->384: 5.36 vs 4.87 ms; the 32 UTMALDG per item serialise per lane), so
+    // it stays an opt-in alternative that the parity tests also cover.
+    static int want_tma = -1;
+    if (want_tma < 0) {
+        const char* e = getenv("B2ME_TC_TMA");
+        want_tma = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    p.tma = 0;
+    if (want_tma && TC_GI == 1 && V_in > 0) {
+        const uint64_t w_rows = (uint64_t)K * (p.nchunk1 + p.nchunk2) * (uint64_t)Cout;
+        bool ok = tc_make_map(&p.tm_in1, in1, (uint64_t)V_in, (uint64_t)Cin1, TC_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ok && Cin2 > 0)
+            ok = tc_make_map(&p.tm_in2, in2, (uint64_t)V_in, (uint64_t)Cin2, TC_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ok)
+            ok = tc_make_map(&p.tm_w, packed_w, w_rows, 64, 64, (uint32_t)(p.n_tile / 2), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (!ok) return B2ME_ELAUNCH;
+        p.tma = 1;
+    }
     size_t smem = fixed + (size_t)S * stage_bytes;
     if (smem < TC_MIN_SMEM) smem = TC_MIN_SMEM;
 

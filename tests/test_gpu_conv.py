@@ -55,7 +55,7 @@ def _call_tc(lib, x, x2, W, nbr, V_out, scale, shift, res, act, out_dtype=torch.
     out = torch.empty((V_out, Cout), dtype=out_dtype, device="cuda")
     import MinkowskiEngine as ME
     masks = ME.tile_masks(nbr, perm, V_out, K) if nbr is not None else None
-    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V_out, Cout,
+    check(lib.b2me_spconv_fwd_tc(ptr(x), c1, ptr(x2), c2, x.shape[0], ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V_out, Cout,
                                  ptr(scale), ptr(shift), ptr(res), act, 0.01, ptr(out), dtype_code(out_dtype),
                                  stream()))
     torch.cuda.synchronize()

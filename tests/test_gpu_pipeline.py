@@ -128,3 +128,38 @@ def test_full_size_batch_independence_and_determinism():
         assert len(C_all) > 600000  # full-size: ~280 k voxels per frame
     finally:
         ME.set_compute_dtype(torch.float32)
+
+
+def test_predict_batch_vs_reference_predict_golden():
+    """The GPU engine against outputs of the reference's OWN InferenceEngine.predict (tests/golden/
+    make_golden_predict.py: unchanged reference model classes + engine on the CPU, seeded weights, MinkUNet18D, ICP and
+    key points off). fp32 networks; labels may differ only on the few points whose top-2 margin is at fp32 noise level
+    (the fixture holds final labels only, so the bound is a fraction), poses within the north-star tolerance."""
+    import os
+    import MinkowskiEngine as ME
+    from conftest import GOLDEN
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig
+    g = np.load(os.path.join(GOLDEN, "reference_predict.npz"))
+    M = make_models(ME)
+    torch.manual_seed(int(g["seed_seg"]))
+    seg = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=3), int(g["seed_seg"])).eval()
+    with torch.no_grad():
+        seg.regression[2].linear.bias.copy_(torch.from_numpy(g["seg_head_bias"]))
+    torch.manual_seed(int(g["seed_rot"]))
+    rot = randomize_bn_stats(M.RobotNetEncode(3, 7), int(g["seed_rot"])).eval()
+    ws = float(sum(v.double().abs().sum() for v in seg.state_dict().values()))
+    assert abs(ws - float(g["seg_weight_sum"])) < 1e-6 * ws
+    eng = BatchedInferenceEngine(seg.cuda(), rot.cuda(), None, cad_points=None,
+                                 config=PipelineConfig(seg_scale=float(g["seg_scale"]), rot_scale=float(g["rot_scale"]),
+                                                       ee_point_counts_threshold=int(g["ee_threshold"]),
+                                                       icp_enabled=False))
+    ME.set_compute_dtype(torch.float32)
+    frames = [(g[f"f{i}_points"], g[f"f{i}_rgb255"]) for i in range(2)]
+    res = eng.predict_batch(frames, ee2base_poses=[g["ee2base"]] * 2)
+    for i, r in enumerate(res):
+        ref = g[f"f{i}_segmentation"]
+        assert (r.segmentation != ref).mean() < 2e-3, (i, (r.segmentation != ref).mean())
+        for mine, gold in ((r.ee_pose, g[f"f{i}_ee_pose"]), (r.base_pose, g[f"f{i}_base_pose"])):
+            Tg, To = G.transformation_matrix(mine), G.transformation_matrix(gold)
+            assert np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < 1e-4, (i, mine, gold)
+            assert G.rotation_angle_deg(Tg[:3, :3], To[:3, :3]) < 0.01, (i, mine, gold)

@@ -70,7 +70,7 @@ def main():
         pairs = int((nbr >= 0).sum()) if nbr is not None else V
 
         def run():
-            check(lib.b2me_spconv_fwd_tc(ptr(x), cin, None, 0, ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V, cout,
+            check(lib.b2me_spconv_fwd_tc(ptr(x), cin, None, 0, x.shape[0], ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V, cout,
                                          None, None, None, 1, 0.0, ptr(out), BF16, stream()))
         run()
         torch.cuda.synchronize()

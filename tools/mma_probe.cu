@@ -50,9 +50,13 @@ __device__ __forceinline__ void commit(uint32_t bar) {
 }
 
 // per round: KSTEPS k-steps x (one MMA of N=n_a and, if n_b, one of N=n_b); commit every `per_commit` rounds
+// wdelay >= 0: warps 1-3 of every CTA stream st.shared.v4 (512 bytes per warp instruction) into a scratch region while
+// the MMAs run, with `wdelay` dependent ALU steps between stores: MMA time per item against competing shared-memory
+// write traffic (out[2] = bytes written by CTA 0, out[3] = cycles the writers ran)
 template <int CG>
 __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, int rounds, int distinct_stages,
-                                                  int commit_each, unsigned long long* out) {
+                                                  int commit_each, unsigned long long* out, int wdelay = -1,
+                                                  const uint8_t* gsrc = nullptr, int amode = 0) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -60,6 +64,8 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
     __shared__ uint64_t bar2[8];
     __shared__ uint64_t bar3;
     __shared__ uint32_t tmem_ptr;
+    __shared__ volatile int stop_flag;
+    if (threadIdx.x == 0) stop_flag = 0;
     uint32_t rank = 0;
     if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,6 +157,100 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
         const long long t2 = clock64();
         if (blockIdx.x == 0) { out[0] = (unsigned long long)(t1 - t0); out[1] = (unsigned long long)(t2 - t0); }
     }
+    if (warp == 0 && lane == 0 && rank == 0 && (wdelay >= 0 || amode)) {
+        stop_flag = 1;
+        if (CG == 2) {  // stop the peer's writers too
+            uint32_t ra;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32((const void*)&stop_flag)), "r"(1u));
+            asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(1u) : "memory");
+        }
+    }
+    // amode bit 1: warp 1 streams cp.async.bulk copies (24 KB each, two in flight, L2-resident source) into scratch
+    // shared memory; bit 2: warps 2-3 stream 16-byte cp.async gathers (8 per thread per round). wdelay = ALU steps
+    // between rounds. These are the async-proxy / LDGSTS write paths the convolution's operand loads use.
+    __shared__ uint64_t wbar[2];
+    if (amode && threadIdx.x == 32) {
+        mbar_init(smem_u32(&wbar[0]), 1);
+        mbar_init(smem_u32(&wbar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (amode && warp == 1 && (amode & 1)) {
+        unsigned long long bytes = 0;
+        uint32_t x = threadIdx.x, i = 0;
+        const long long t0 = clock64();
+        __syncwarp();
+        while (!stop_flag) {
+            const uint32_t b = i & 1u;
+            if (i >= 2) mbar_wait(smem_u32(&wbar[b]), ((i >> 1) - 1) & 1u);
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&wbar[b])), "r"(24576u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(base + 120u * 1024u + b * 24576u), "l"(gsrc + (size_t)((i * 7u + blockIdx.x) & 31u) * 24576u),
+                               "r"(24576u), "r"(smem_u32(&wbar[b])) : "memory");
+            }
+            __syncwarp();
+            ++i;
+            bytes += 24576;
+            for (int d = 0; d < wdelay; ++d) x = x * 1664525u + 1013904223u;
+        }
+        // drain
+        if (i >= 1) mbar_wait(smem_u32(&wbar[(i - 1) & 1u]), (((i - 1) >> 1)) & 1u);
+        if (i >= 2) mbar_wait(smem_u32(&wbar[(i - 2) & 1u]), (((i - 2) >> 1)) & 1u);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && lane == 0) {
+            atomicAdd(&out[2], bytes + (x == 0xdeadbeefu));
+            out[3] = (unsigned long long)(t1 - t0);
+        }
+    } else if (amode && warp >= 2 && (amode & 2)) {
+        const uint32_t scratch = base + 168u * 1024u + (uint32_t)(warp - 1) * 8192u;
+        unsigned long long bytes = 0;
+        uint32_t x = threadIdx.x * 2654435761u, i = 0;
+        const long long t0 = clock64();
+        while (!stop_flag) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                // 8 lanes fetch one 128-byte row from a pseudo-random place of a 32 MB window (L2-resident)
+                const uint32_t row = (x >> 3) + (uint32_t)u * 977u + (uint32_t)(lane >> 3) * 131u;
+                const uint8_t* g = gsrc + ((size_t)(row & 0x3FFFFu) * 128u) + (uint32_t)(lane & 7) * 16u;
+                const uint32_t dst = scratch + (uint32_t)u * 512u + (uint32_t)lane * 16u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            ++i;
+            bytes += 8 * 512;
+            x = x * 1664525u + 1013904223u;
+            x = __shfl_sync(0xffffffffu, x, 0);
+            for (int d = 0; d < wdelay; ++d) x = x * 1664525u + 1013904223u;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && lane == 0) {
+            atomicAdd(&out[4], bytes + (x == 0xdeadbeefu));
+            if (warp == 2) out[5] = (unsigned long long)(t1 - t0);
+        }
+    }
+    if (!amode && warp >= 1 && wdelay >= 0) {
+        const uint32_t scratch = base + 168u * 1024u + (uint32_t)(warp - 1) * 8192u;
+        unsigned long long bytes = 0;
+        uint32_t x = threadIdx.x, i = 0;
+        const long long t0 = clock64();
+        while (!stop_flag) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {  // 16 independent 512-byte stores per flag check
+                const uint32_t dst = scratch + (uint32_t)u * 512u + (uint32_t)lane * 16u;
+                asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(x) : "memory");
+            }
+            ++i;
+            bytes += 16 * 512;
+            for (int d = 0; d < wdelay; ++d) x = x * 1664525u + 1013904223u;
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && lane == 0) {
+            atomicAdd(&out[2], bytes + (x == 0xdeadbeefu));
+            if (warp == 1) out[3] = (unsigned long long)(t1 - t0);
+        }
+    }
     if (CG == 2 && rank == 1 && threadIdx.x == 0) mbar_wait(smem_u32(&bar), 0);  // multicast commit reaches the peer too
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
@@ -167,9 +267,12 @@ __global__ void __launch_bounds__(128, 1) k_probe(int n_a, int n_b, int ksteps, 
 }
 
 template <int CG>
-static void run(int n_a, int n_b, int grid, int stages, int commit_each) {
+static void run(int n_a, int n_b, int grid, int stages, int commit_each, int wdelay = -1, int amode = 0) {
     unsigned long long* d;
-    cudaMalloc(&d, 16);
+    cudaMalloc(&d, 64);
+    cudaMemset(d, 0, 64);
+    static uint8_t* gsrc = nullptr;
+    if (!gsrc) { cudaMalloc(&gsrc, 34u << 20); cudaMemset(gsrc, 0, 34u << 20); }
     const int ksteps = 4, rounds = 2000;
     const size_t smem = 201 * 1024 + 1024;
     cudaFuncSetAttribute(k_probe<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -184,10 +287,16 @@ static void run(int n_a, int n_b, int grid, int stages, int commit_each) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_probe<CG>, n_a, n_b, ksteps, rounds, stages, commit_each, d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_probe<CG>, n_a, n_b, ksteps, rounds, stages, commit_each, d, wdelay,
+                                       (const uint8_t*)gsrc, amode);
     cudaError_t e2 = cudaDeviceSynchronize();
-    unsigned long long h[2] = {0, 0};
-    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+    if (amode)
+        printf("  [async writers mode %d delay %d: bulk %.1f B/cyc, cp.async %.1f B/cyc per SM] ", amode, wdelay,
+               h[3] ? (double)h[2] / (double)h[3] : 0.0, h[5] ? (double)h[4] / (double)h[5] : 0.0);
+    else if (wdelay >= 0)
+        printf("  [writers: delay %d, %.1f B/cycle of st.shared per SM] ", wdelay, h[3] ? (double)h[2] / (double)h[3] : 0.0);
     const double n_mma = (double)rounds * ksteps * (n_b ? 2 : 1);
     const double flop_per_sm = (double)rounds * ksteps * 2.0 * 128 * (n_a + n_b) * 16;
     printf("cta_group::%d grid %3d N=%3d+%3d stages %d commit/fence %d: issue %.1f cyc/MMA, complete %.1f cyc/MMA, %.0f cyc per 64-K item, "
@@ -196,7 +305,24 @@ static void run(int n_a, int n_b, int grid, int stages, int commit_each) {
     cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 'a') {
+        // async-proxy contention sweep (the convolution's operand load paths) against the 256 + 128 instruction pair
+        run<2>(256, 128, 148, 3, 1);
+        for (int am : {1, 2, 3})
+            for (int wd : {2048, 512, 128, 0}) run<2>(256, 128, 148, 3, 1, wd, am);
+        run<2>(256, 128, 2, 3, 1);
+        for (int wd : {512, 0}) run<2>(256, 128, 2, 3, 1, wd, 3);
+        return 0;
+    }
+    if (argc > 1 && argv[1][0] == 's') {
+        // shared-memory contention sweep: the 256 + 128 instruction pair on every SM against st.shared write streams
+        for (int grid : {2, 148})
+            for (int wd : {-1, 1024, 512, 256, 128, 64, 32, 16, 0}) run<2>(256, 128, grid, 3, 1, wd);
+        for (int wd : {-1, 256, 64, 0}) run<2>(128, 0, 148, 3, 1, wd);
+        for (int wd : {-1, 256, 64, 0}) run<2>(256, 0, 148, 3, 1, wd);
+        return 0;
+    }
     // bits: 1 commit per item, 2 fence.proxy.async, 8 shared-memory poll, 16 mbarrier test_wait, 32 tcgen05.fence::after
     for (int ce : {0, 1, 3, 1 + 8, 1 + 16, 1 + 32, 1 + 2 + 16 + 32}) run<2>(256, 128, 2, 3, ce);
     return 0;

@@ -50,6 +50,7 @@ def parse():
                     help="key-point network: 6-class MinkUNet18D (default; both arms) or the reference's default "
                          "PointNet2SSG branch on GPU-native FPS / ball query / 3-NN (B200 arm only)")
     ap.add_argument("--mask-block", type=int, default=None, help="rows per locality block of the K3b mask sort (0 = global)")
+    ap.add_argument("--mask-two-level", action="store_true", help="A/B: two-level K3b mask-sort keys (default: one-level)")
     ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     return ap.parse_args()
 
@@ -212,6 +213,8 @@ def run_b200(args, rank, world, local):
     ME.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     if args.mask_block is not None:
         ME.set_mask_sort_block(args.mask_block)
+    if args.mask_two_level:
+        ME.set_mask_sort_two_level(True)
     seg, rot, kp = [m.to(dev) for m in build_models(ME, kp_backbone=args.kp_backbone)]
     cad = torch.from_numpy(ee_surface_cloud(4096, SEED)).to(dev)
     cfg = PipelineConfig(seg_scale=args.scale, icp_enabled=not args.no_icp)
@@ -309,7 +312,7 @@ def run_b200(args, rank, world, local):
 
     # ---- roofline of the dominant kernel (k_spconv_tc): FLOPs from the census / CUDA-event durations
     per_step = len(recs_census)
-    tc_flops = tc_ms = simt_ms = 0.0
+    tc_flops = tc_ms = simt_ms = tc_exec = 0.0
     all_ms = 0.0
     n_tc = 0
     torch.cuda.synchronize()
@@ -319,6 +322,7 @@ def run_b200(args, rank, world, local):
         all_ms += ms
         if c["kind"] == "tc":
             tc_flops += 2.0 * c["pairs"] * c["Cin"] * c["Cout"]
+            tc_exec += 2.0 * c.get("passes", 0) * 256.0 * c["Cin"] * c["Cout"]
             tc_ms += ms
             n_tc += 1
         else:
@@ -331,6 +335,9 @@ def run_b200(args, rank, world, local):
             c["ms"] = float(np.mean(ms))
             c["tflops"] = 2.0 * c["pairs"] * c["Cin"] * c["Cout"] / (c["ms"] * 1e-3) / 1e12
             c["fill"] = c["pairs"] / max(1, c["K"] * c["V_out"])
+            if c.get("passes"):
+                c["row_efficiency"] = c["pairs"] / (c["passes"] * 256.0)
+                c["mma_tflops"] = 2.0 * c["passes"] * 256.0 * c["Cin"] * c["Cout"] / (c["ms"] * 1e-3) / 1e12
             tab.append(c)
         json.dump(tab, open(args.conv_table, "w"))
     peaks = load_peaks()
@@ -343,7 +350,11 @@ def run_b200(args, rank, world, local):
                 "launches_per_step": n_tc // max(args.steps, 1),
                 "share_of_step": tc_ms / ms_dev if world == 1 else None,
                 "simt_conv_share_of_step": simt_ms / ms_dev if world == 1 else None,
-                "flops_per_step": tc_flops / max(args.steps, 1)}
+                "flops_per_step": tc_flops / max(args.steps, 1),
+                # what the tensor pipe actually executes: every (256-row tile pair, offset) pass runs full M = 256 MMAs,
+                # rows without that neighbour are zero-filled (not counted in `achieved`)
+                "mma_executed": tc_exec / (tc_ms * 1e-3) / 1e12,
+                "row_efficiency": tc_flops / tc_exec if tc_exec > 0 else None}
 
     if rank != 0:
         return

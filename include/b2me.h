@@ -118,6 +118,12 @@ int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* tab
  */
 int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
                         b2me_stream_t stream);
+/* Two-level keys (K = 27 maps): the 10 rarest offsets of the map form the most significant part as above, the other
+ * offsets are ordered per segment by their frequency among the rows of that segment. Fewer (tile, offset) passes than
+ * the one-level keys; same contract otherwise. ws: >= b2me_mask_sort_keys2_ws_bytes(V). */
+size_t b2me_mask_sort_keys2_ws_bytes(int64_t V);
+int b2me_mask_sort_keys2(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
+                         b2me_stream_t stream);
 /* 64-bit keys with a locality prefix: key[row] = (row / block_rows) << 32 | mask key (block_rows = 0: no prefix).
  * Rows of one block of consecutive first-occurrence rows stay together, so concurrently running tiles gather from
  * one L2-sized window of the input. */

@@ -42,6 +42,9 @@ class _State:
     mask_sort = True  # tcgen05 convolutions take a neighbour-mask-sorted row permutation (tile-level offset skipping)
     mask_sort_min_rows = 32768  # smaller maps keep their natural row order (the sort costs more than it saves)
     mask_sort_block = 0  # rows per locality block of that sort, 0 = whole map (measured: 0 is fastest)
+    # K = 27 maps: per-segment order of the common offsets (b2me_mask_sort_keys2). Off by default: at 32 frames the
+    # one-level order already reaches 0.885 row efficiency (two-level 0.901: conv -1 ms, key kernels +5 ms per step)
+    mask_sort_two_level = False
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     profile = None  # bench.py hook, see ops._profile_conv
@@ -73,6 +76,11 @@ def set_mask_sort(flag):
     _State.mask_sort = bool(flag)
 
 
+def set_mask_sort_two_level(on):
+    """A/B switch: two-level (True, default) or one-level (False) mask-sort keys for the K = 27 maps."""
+    _State.mask_sort_two_level = bool(on)
+
+
 def set_mask_sort_block(rows):
     """rows of one locality block of the mask sort (0 = sort the whole map by mask only)."""
     _State.mask_sort_block = int(rows)
@@ -84,7 +92,13 @@ def mask_sorted_perm(nbr, V, K, block_rows=None):
     if block_rows is None:
         block_rows = _State.mask_sort_block
     ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
-    if block_rows == 0:  # mask-only keys fit 32 bits: half the radix passes of the device sort
+    if block_rows == 0 and _State.mask_sort_two_level and K == 27:
+        # two-level keys: global rarest-first segment + per-segment order of the remaining offsets
+        ws = torch.empty((lib.b2me_mask_sort_keys2_ws_bytes(V),), dtype=torch.uint8, device=nbr.device)
+        keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
+        check(lib.b2me_mask_sort_keys2(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys2")
+        _count(2)
+    elif block_rows == 0:  # mask-only keys fit 32 bits: half the radix passes of the device sort
         keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
         check(lib.b2me_mask_sort_keys(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys")
     else:

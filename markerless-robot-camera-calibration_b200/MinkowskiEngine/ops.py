@@ -92,15 +92,24 @@ def _run_elt(p):
     return out
 
 
-def _profile_conv(kind, p, Cin):
-    """bench.py hook: 'census' records the algorithmic work of every convolution launch (pairs = sum_k P_k),
+def _profile_conv(kind, p, Cin, masks=None):
+    """bench.py hook: 'census' records the algorithmic work of every convolution launch (pairs = sum_k P_k) and, for
+    the tcgen05 kernel, the (256-row tile pair, offset) passes it executes (zero-filled rows included),
     'events' brackets the launch with CUDA events on the launching stream."""
     prof = _State.profile
     if prof is None:
         return None
     if prof["mode"] == "census":
         pairs = int((p.nbr >= 0).sum().item()) if p.nbr is not None else int(p.V_out)
-        prof["records"].append(dict(kind=kind, K=p.K, Cin=Cin, Cout=p.Cout, V_out=int(p.V_out), pairs=pairs))
+        rec = dict(kind=kind, K=p.K, Cin=Cin, Cout=p.Cout, V_out=int(p.V_out), pairs=pairs)
+        if kind == "tc":
+            tiles = (int(p.V_out) + 255) // 256
+            if masks is not None:
+                m = masks[:tiles].to(torch.int64) & 0xFFFFFFFF
+                rec["passes"] = int(sum(int(((m >> k) & 1).sum().item()) for k in range(p.K)))
+            else:
+                rec["passes"] = tiles * p.K
+        prof["records"].append(rec)
         return None
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
@@ -129,7 +138,7 @@ def _run_conv(p):
         packed = _weight_packed(p.module, K, Cin1, Cin2, Cout)
         out = torch.empty((V_out, Cout), dtype=torch.bfloat16, device=dev)
         perm, masks = p.perm() if p.perm is not None else (None, None)
-        ev = _profile_conv("tc", p, Cin1 + Cin2)
+        ev = _profile_conv("tc", p, Cin1 + Cin2, masks)
         check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, f1.shape[0], ptr(packed), ptr(p.nbr), ptr(perm), ptr(masks), K,
                                      V_out, Cout, ptr(p.scale), ptr(p.shift), ptr(res), p.act, p.slope, ptr(out),
                                      _lib.BF16, stream()), "spconv_fwd_tc")

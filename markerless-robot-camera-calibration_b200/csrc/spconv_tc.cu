@@ -493,53 +493,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
 
     if (warp < 4 && p.tma) {
         // =============================== gather producers, TMA mode ===============================
-        // warp w owns rows 32 w .. 32 w + 31 of the CTA's tile: lanes 0-7 each issue ONE tile::gather4 per item (4
-        // rows x 128 bytes straight into the swizzled image; absent neighbours = row -1 = out of bounds = zeros), lanes
-        // 8-31 prefetch the next offset's rows into L2. Four warps = four schedulers issue the 32 UTMALDG of an item.
+        // warp w owns rows 32 w .. 32 w + 31 of the CTA's tile. Lane l reads the neighbour index of row 32 w + l; per
+        // item the warp issues 8 tile::gather4 copies (4 rows x 128 bytes each, straight into the swizzled image;
+        // absent neighbours = row -1 = out of bounds = zeros) from shfl-broadcast, i.e. warp-uniform, operands, so each
+        // UTMALDG takes its operands from uniform registers without a per-lane serialisation loop.
         const uint32_t full_leader = mapa_u32(bar_full, 0u);
-        const int r0 = 32 * warp + 4 * lane;        // lanes 0-7: first of this lane's 4 rows
-        const int tp = 24 * warp + lane - 8;        // lanes 8-31: prefetch thread id 0..95
         int ist = 0, iph = 0, it = 0;
-        uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
+        uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.total_work ? tile_mask(unit0) : 0u, 0);
         for (int w = unit0; w < p.total_work; w += G, ++it) {
             const uint32_t kmask = kmask_next;
-            if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+            if (w + G < p.total_work) kmask_next = __shfl_sync(0xffffffffu, tile_mask(w + G), 0);
             mbar_wait(bar_nbr_full, (uint32_t)it & 1u);
 #pragma unroll 1
-            for (int k = 0; k < KT; ++k) {
-                if (!((kmask >> k) & 1u)) continue;
-                int id0 = -1, id1 = -1, id2 = -1, id3 = -1;
-                if (lane < 8) {
-                    id0 = nbr_s[(r0 + 0) * KT + k];
-                    id1 = nbr_s[(r0 + 1) * KT + k];
-                    id2 = nbr_s[(r0 + 2) * KT + k];
-                    id3 = nbr_s[(r0 + 3) * KT + k];
-                }
-                if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
+            for (uint32_t m = kmask; m; m &= m - 1u) {
+                const int k = __ffs((int)m) - 1;
+                const int id = nbr_s[(32 * warp + lane) * KT + k];
+                int ids[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) ids[q] = __shfl_sync(0xffffffffu, id, q);
+                if ((m & (m - 1u)) == 0u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH && lane >= 8) {
-                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
-                    for (int L = tp; L < TC_BM * nchunk; L += 96) {
-                        const int r = L / nchunk, ch = L - r * nchunk;
-                        const int id = nbr_s[r * KT + k2];
-                        if (id >= 0) {
-                            if (ch < p.nchunk1) prefetch_l2(p.in1 + (long long)id * p.Cin1 + ch * TC_BK);
-                            else prefetch_l2(p.in2 + (long long)id * p.Cin2 + (ch - p.nchunk1) * TC_BK);
-                        }
+                } else if (TC_L2_PREFETCH) {
+                    // pull the rows of the NEXT offset into L2 one whole offset (= nchunk items) ahead of their gather
+                    const uint32_t m2 = m & (m - 1u);
+                    const int k2 = __ffs((int)m2) - 1;
+                    const int id2 = nbr_s[(32 * warp + lane) * KT + k2];
+                    if (id2 >= 0) {
+                        for (int ch = 0; ch < p.nchunk1; ++ch) prefetch_l2(p.in1 + (long long)id2 * p.Cin1 + ch * TC_BK);
+                        for (int ch = 0; ch < p.nchunk2; ++ch) prefetch_l2(p.in2 + (long long)id2 * p.Cin2 + ch * TC_BK);
                     }
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
                     mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u);
-                    if (lane < 8) {
-                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes + (uint32_t)r0 * 128u;
-                        if (c < p.nchunk1)
-                            tma_gather4_pair(a_s, &p.tm_in1, c * TC_BK, id0, id1, id2, id3, full_leader + 8 * ist);
-                        else
-                            tma_gather4_pair(a_s, &p.tm_in2, (c - p.nchunk1) * TC_BK, id0, id1, id2, id3,
-                                             full_leader + 8 * ist);
+                    if (tc_elect_one()) {
+                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes + (uint32_t)(32 * warp) * 128u;
+                        const CUtensorMap* tm = c < p.nchunk1 ? &p.tm_in1 : &p.tm_in2;
+                        const int col = (c < p.nchunk1 ? c : c - p.nchunk1) * TC_BK;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            tma_gather4_pair(a_s + (uint32_t)g * 512u, tm, col, ids[4 * g], ids[4 * g + 1],
+                                             ids[4 * g + 2], ids[4 * g + 3], full_leader + 8 * ist);
                     }
+                    __syncwarp();
                     if (++ist == S) { ist = 0; iph ^= 1; }
                 }
             }
@@ -675,7 +672,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         tc_fence_after();
                         const uint32_t a_lo = a_lo0 + (uint32_t)st * stage_lo;
                         if (tc_elect_one()) {
+#if defined(B2ME_TC_PROFILE) || defined(B2ME_TC_EXPERIMENT)
+                            if (need_fence && !(p.debug & 8)) fence_proxy_async();  // 8: timing experiment only
+#else
                             if (need_fence) fence_proxy_async();
+#endif
                             // the two instructions of a K step share the A slice; both read it from shared memory
                             // (keeping it in the collector buffer, collector::a::fill / lastuse, was measured slower)
                             for (int kk = 0; kk < ks; ++kk) {
@@ -1319,7 +1320,7 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     while (S >= 2 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
     if (S < 2) return B2ME_EUNSUPPORTED;
     p.debug = 0;
-#ifdef B2ME_TC_PROFILE
+#if defined(B2ME_TC_PROFILE) || defined(B2ME_TC_EXPERIMENT)
     if (const char* e = getenv("B2ME_TC_DEBUG")) p.debug = atoi(e);
     if (const char* e = getenv("B2ME_TC_STAGES")) {  // debug build only: ring-depth experiments
         const int want = atoi(e);

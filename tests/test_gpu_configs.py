@@ -133,3 +133,49 @@ def test_cluster_dense_blob_and_near_threshold_gaps():
         want = np.sort(G.largest_cluster(p, 0.06))
         assert np.array_equal(got, want), f"segment {s}: {len(got)} vs {len(want)}"
         assert int(sizes[s]) == len(want)
+
+
+def test_mask_sort_keys_match_definition():
+    """K3b keys (one- and two-level) against the NumPy statement of their definition (oracle/mask_sort.py), bit-exact,
+    on random maps and on the k3 map of a synthetic frame; on the frame the two-level order needs fewer (tile, offset)
+    passes than the one-level order, which needs far fewer than the natural order."""
+    import MinkowskiEngine as ME
+    from MinkowskiEngine._lib import lib, ptr, stream, check
+    from oracle import mask_sort as MS
+
+    def device_keys(nbr_c, two_level):
+        V, K = nbr_c.shape
+        keys = torch.empty(V, dtype=torch.int32, device="cuda")
+        if two_level:
+            ws = torch.empty(lib.b2me_mask_sort_keys2_ws_bytes(V), dtype=torch.uint8, device="cuda")
+            check(lib.b2me_mask_sort_keys2(ptr(nbr_c), V, K, ptr(keys), ptr(ws), ws.numel(), stream()))
+        else:
+            ws = torch.empty(128, dtype=torch.uint8, device="cuda")
+            check(lib.b2me_mask_sort_keys(ptr(nbr_c), V, K, ptr(keys), ptr(ws), ws.numel(), stream()))
+        return keys.cpu().numpy()
+
+    g = torch.Generator().manual_seed(9)
+    cases = []
+    for V, K, p in ((1, 27, 0.5), (300, 27, 0.7), (20000, 27, 0.72), (5000, 8, 0.6)):
+        nbr = torch.randint(0, V, (V, K), generator=g).int()
+        # offsets with very different frequencies, some never / always present
+        drop = torch.rand(V, K, generator=g) < (p * torch.linspace(0.2, 1.3, K)).clamp(max=1.0)
+        nbr[drop] = -1
+        nbr[:, K // 2] = torch.arange(V, dtype=torch.int32)
+        cases.append(nbr)
+    f = make_frame(311, width=320, height=240)
+    fld = ME.TensorField(features=torch.from_numpy(f["rgb"]).cuda(),
+                         coordinates=ME.utils.batched_coordinates([torch.from_numpy(f["points"]) * 200.0],
+                                                                  dtype=torch.float32), device="cuda")
+    sp = fld.sparse()
+    frame_nbr = sp.coordinate_manager.kernel_map_k3(sp.coordinate_map_key)[:sp.C.shape[0]].cpu()
+    cases.append(frame_nbr)
+    for nbr in cases:
+        n = nbr.numpy()
+        assert np.array_equal(device_keys(nbr.cuda(), False), MS.keys_one_level(n)), nbr.shape
+        assert np.array_equal(device_keys(nbr.cuda(), True), MS.keys_two_level(n)), nbr.shape
+    n = frame_nbr.numpy()
+    p_nat = MS.passes(n, np.arange(len(n)))
+    p_one = MS.passes(n, np.argsort(MS.keys_one_level(n), kind="stable"))
+    p_two = MS.passes(n, np.argsort(MS.keys_two_level(n), kind="stable"))
+    assert p_two < p_one < 0.6 * p_nat, (p_nat, p_one, p_two)

@@ -51,6 +51,9 @@ def parse():
                          "PointNet2SSG branch on GPU-native FPS / ball query / 3-NN (B200 arm only)")
     ap.add_argument("--mask-block", type=int, default=None, help="rows per locality block of the K3b mask sort (0 = global)")
     ap.add_argument("--mask-two-level", action="store_true", help="A/B: two-level K3b mask-sort keys (default: one-level)")
+    ap.add_argument("--cprofile", default=None, help="one extra (untimed) step under cProfile: host-side launch cost (text)")
+    ap.add_argument("--torch-profile", default=None,
+                    help="one extra (untimed) step under torch.profiler: per-kernel device times + GPU busy fraction (text)")
     ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     return ap.parse_args()
 
@@ -301,6 +304,41 @@ def run_b200(args, rank, world, local):
         step_device()
         stage_ms = {k: round(v, 3) for k, v in eng.stage_times.items()}
         eng.stage_times = None
+
+    if args.cprofile and rank == 0:
+        # developer aid: where the HOST spends its time while launching one step (the GPU idles when it falls behind)
+        import cProfile
+        import pstats
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        step_device()
+        pr.disable()
+        t_launch = (time.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        t_total = (time.perf_counter() - t0) * 1e3
+        with open(args.cprofile, "w") as fp:
+            fp.write(f"one step of {args.frames} frames: host returned after {t_launch:.1f} ms, GPU done after {t_total:.1f} ms\n")
+            pstats.Stats(pr, stream=fp).sort_stats("cumulative").print_stats(45)
+            pstats.Stats(pr, stream=fp).sort_stats("tottime").print_stats(30)
+
+    if args.torch_profile and rank == 0:
+        # developer aid: device time per kernel of ONE step as CUPTI sees it (no replay, warm caches) and how much of
+        # the step the GPU had a kernel running (the rest is host launch / sync latency)
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_device()
+            torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ka = prof.key_averages()
+        busy_ms = sum(getattr(k, "device_time_total", getattr(k, "cuda_time_total", 0)) for k in ka) / 1e3
+        with open(args.torch_profile, "w") as fp:
+            fp.write(f"one step of {args.frames} frames under torch.profiler: wall {wall_ms:.1f} ms, "
+                     f"sum of kernel device time {busy_ms:.1f} ms ({100 * busy_ms / wall_ms:.1f} % busy)\n")
+            fp.write(ka.table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60))
 
     # ---- the only collective: all-gather of the per-frame records (outside the per-step loop, as in production)
     recs = bdist.pack_records(list(range(rank * args.frames, (rank + 1) * args.frames)), results)

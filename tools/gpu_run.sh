@@ -1,9 +1,19 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-export B2ME_LIB_PATH=$GRAFT_REPO_ROOT/markerless-robot-camera-calibration_b200/lib_debug/libb2me.so
-SH=27:384:384,27:256:256,1:416:384
-for cfg in "0 9" "8 9" "0 3" "0 2" "0 9" "8 9"; do
-  set -- $cfg
-  echo "== DEBUG=$1 STAGES=$2"
-  B2ME_TC_DEBUG=$1 B2ME_TC_STAGES=$2 timeout 300 python tools/conv_probe.py --frames 8 --shapes $SH 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_model.py -x -q -m gpu > gpurun_out/pytest_epi.log 2>&1; echo "conv+model rc=$?"
+tail -3 gpurun_out/pytest_epi.log
+SH=27:384:384,1:416:384,8:384:384,1:256:1024,27:128:128,27:256:256
+for v in new old new old; do
+  echo "== $v"
+  if [ $v = old ]; then export B2ME_LIB_PATH=$GRAFT_REPO_ROOT/markerless-robot-camera-calibration_b200/lib_debug/libb2me.so; else unset B2ME_LIB_PATH; fi
+  timeout 300 python tools/conv_probe.py --frames 8 --shapes $SH 2>&1 | tail -6
+done
+for v in new old; do
+  echo "== bench $v"
+  if [ $v = old ]; then export B2ME_LIB_PATH=$GRAFT_REPO_ROOT/markerless-robot-camera-calibration_b200/lib_debug/libb2me.so; else unset B2ME_LIB_PATH; fi
+  timeout 300 python bench.py --frames 32 --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.readline())
+r = d['roofline']
+print(d['value'], d['ms_per_step'], 'alg', r['achieved'], 'frac', r['frac'], 'exec', r['mma_executed'], 'share', r['share_of_step'])"
 done

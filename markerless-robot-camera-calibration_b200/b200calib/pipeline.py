@@ -48,6 +48,11 @@ class PipelineConfig:
     kp_center_at_origin: bool = True
     translation_x_offset: float = -0.015
     num_dense_points: int = 2048   # INFERENCE.num_of_dense_input_points (PointNet++ key-point branch)
+    # is_confident = check_sanity(...) as in app/inference_engine.py:323 (host NumPy on the EE crop, b200calib/sanity.py;
+    # predict_batch only: it needs the host copy of the points). Off: is_confident = "a pose was produced".
+    sanity_check: bool = False
+    sanity_min_ee_points: int = 2048      # INFERENCE.SANITY.min_num_of_ee_points
+    sanity_kp_error_margin: float = 0.05  # INFERENCE.KEY_POINTS.error_margin
 
 
 @dataclass
@@ -278,7 +283,7 @@ class BatchedInferenceEngine:
                     ee_T, stats = icp_p2p_batched(self.cad, pts, soffs, ee_T)
         # --- one device->host transfer of everything the host needs
         with _Stage(self, "readback"):
-            pack = [ee_T.reshape(S, 16)]
+            pack = [ee_T.reshape(S, 16), ee_pose]   # ee_pose: before the ICP refinement (what check_sanity looks at)
             if stats is not None:
                 pack.append(stats)
             if kp_T is not None:
@@ -287,8 +292,10 @@ class BatchedInferenceEngine:
                 if kstats is not None:
                     pack.append(kstats)
             host = torch.cat(pack, dim=1).cpu().numpy()
-            c = 16
+            c = 23
             res["ee_T"] = host[:, :16].reshape(S, 4, 4)
+            res["ee_pose_initial"] = host[:, 16:23]
+            res["kp_threshold"] = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
             if stats is not None:
                 res["icp_stats"] = host[:, c:c + 4]
                 c += 4
@@ -355,6 +362,7 @@ class BatchedInferenceEngine:
             seg_labels = labels2
         pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)
         pose["ee_counts"] = (ee_offs[1:] - ee_offs[:-1]).numpy()
+        pose["crop_labels"] = labels2   # device tensor: the labels the EE crop was taken from (2 = the kept EE cluster)
         return seg_labels, pose
 
     @torch.no_grad()
@@ -367,7 +375,31 @@ class BatchedInferenceEngine:
         if gt_labels is not None:
             gl = torch.as_tensor(np.concatenate(gt_labels).astype(np.uint8)).to(dev)
         seg_labels, pose = self.predict_device(points, rgb, bidx, offs, ee2base_poses, gl, kp_conf_threshold)
-        return self.assemble(seg_labels.cpu().numpy(), offs, pose, ee2base_poses)
+        results = self.assemble(seg_labels.cpu().numpy(), offs, pose, ee2base_poses)
+        if self.cfg.sanity_check:
+            self.apply_sanity(results, frames, offs, pose)
+        return results
+
+    def apply_sanity(self, results, frames, offs, pose):
+        """is_confident as the reference sets it (app/inference_engine.py:323): check_sanity on the frame's points, the
+        labels the EE crop came from, the EE pose BEFORE the ICP refinement and the selected key points."""
+        from .sanity import check_sanity
+        crop = pose["crop_labels"].cpu().numpy()
+        for j, f in enumerate(pose["ok_frames"]):
+            r = results[f]
+            if r.ee_pose is None:
+                continue
+            pts_f = np.asarray(frames[f][0])
+            lab_f = crop[offs[f]:offs[f + 1]]
+            kps = []
+            if pose.get("key_points") is not None:
+                probs, idx, _ = pose["key_points"]
+                ee_pts = pts_f[lab_f == 2]
+                for k in np.nonzero(probs[j] > pose["kp_threshold"])[0]:
+                    kps.append((int(k), ee_pts[idx[j, k]]))
+            r.key_points = kps
+            r.is_confident = bool(check_sanity(pts_f, lab_f, pose["ee_pose_initial"][j], kps,
+                                               self.cfg.sanity_min_ee_points, self.cfg.sanity_kp_error_margin))
 
     @staticmethod
     def assemble(seg_h, offs, pose, ee2base_poses=None):

@@ -163,3 +163,37 @@ def test_predict_batch_vs_reference_predict_golden():
             Tg, To = G.transformation_matrix(mine), G.transformation_matrix(gold)
             assert np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < 1e-4, (i, mine, gold)
             assert G.rotation_angle_deg(Tg[:3, :3], To[:3, :3]) < 0.01, (i, mine, gold)
+
+
+def test_predict_batch_sanity_check_wiring(setup):
+    """PipelineConfig.sanity_check: is_confident is check_sanity (b200calib/sanity.py, pinned by the reference's own
+    outputs in tests/test_sanity_golden.py) of the frame's points, the crop labels, the EE pose before ICP and the
+    selected key points - recomputed here from what the engine returns."""
+    ME, o, c, frames = setup
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig
+    from b200calib.sanity import check_sanity
+    cad = ee_surface_cloud(2048, 13)
+    eng = BatchedInferenceEngine(c["seg"], c["rot"], c["kp"], cad_points=torch.from_numpy(cad).cuda(),
+                                 config=PipelineConfig(seg_scale=100.0, rot_scale=200.0, kp_scale=400.0,
+                                                       ee_point_counts_threshold=128, kp_conf_threshold=0.0,
+                                                       sanity_check=True, sanity_min_ee_points=128))
+    ME.set_compute_dtype(torch.float32)
+    fr = [(f["points"], f["rgb"]) for f in frames]
+    gl = [f["labels"] for f in frames]
+    points, rgb, bidx, offs = __import__("b200calib.pipeline", fromlist=["batch_frames"]).batch_frames(fr, torch.device("cuda"))
+    res = eng.predict_batch(fr, gt_labels=gl)
+    # independent recomputation from a second run's raw pose dictionary
+    glt = torch.as_tensor(np.concatenate(gl).astype(np.uint8)).cuda()
+    _, pose = eng.predict_device(points, rgb, bidx, offs, None, glt, None)
+    crop = pose["crop_labels"].cpu().numpy()
+    seen = 0
+    for j, f in enumerate(pose["ok_frames"]):
+        lab = crop[offs[f]:offs[f + 1]]
+        ee_pts = fr[f][0][lab == 2]
+        probs, idx, _ = pose["key_points"]
+        kps = [(int(k), ee_pts[idx[j, k]]) for k in np.nonzero(probs[j] > 0.0)[0]]
+        want = check_sanity(fr[f][0], lab, pose["ee_pose_initial"][j], kps, 128, 0.05)
+        assert res[f].is_confident == bool(want)
+        assert len(res[f].key_points) == len(kps)
+        seen += 1
+    assert seen >= 2

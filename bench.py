@@ -77,6 +77,19 @@ def make_workload(n_frames, rank, width, height):
     return [_gen_frame(s) for s in seeds]
 
 
+def load_traffic(frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_spconv_tc launch (mean over the 121 launches of one step), from
+    the committed ncu capture of this command at 32 frames (profiles/r01_k_spconv_tc_dram_traffic.json); None for
+    another batch size or when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_k_spconv_tc_dram_traffic.json")
+    try:
+        with open(path) as fp:
+            t = json.load(fp)
+        return float(t["dram_bytes_per_launch"]) if int(t.get("frames", -1)) == int(frames) else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -383,7 +396,8 @@ def run_b200(args, rank, world, local):
     if tc_ms > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
         roof = {"kernel": "k_spconv_tc (tcgen05 gather-GEMM sparse convolution)", "bound": "tensor", "achieved": ach,
-                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                "traffic": load_traffic(args.frames),
                 "peak_source": f"{peaks['src']} bf16 sustained (burst {peaks['tf_burst']})",
                 "launches_per_step": n_tc // max(args.steps, 1),
                 "share_of_step": tc_ms / ms_dev if world == 1 else None,

@@ -50,6 +50,7 @@ def parse():
                     help="key-point network: 6-class MinkUNet18D (default; both arms) or the reference's default "
                          "PointNet2SSG branch on GPU-native FPS / ball query / 3-NN (B200 arm only)")
     ap.add_argument("--mask-block", type=int, default=None, help="rows per locality block of the K3b mask sort (0 = global)")
+    ap.add_argument("--mask-morton", action="store_true", help="A/B: Morton order inside a mask group of the k3 maps")
     ap.add_argument("--mask-two-level", action="store_true", help="A/B: two-level K3b mask-sort keys (default: one-level)")
     ap.add_argument("--cprofile", default=None, help="one extra (untimed) step under cProfile: host-side launch cost (text)")
     ap.add_argument("--torch-profile", default=None,
@@ -229,6 +230,8 @@ def run_b200(args, rank, world, local):
     ME.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     if args.mask_block is not None:
         ME.set_mask_sort_block(args.mask_block)
+    if args.mask_morton:
+        ME.set_mask_sort_morton(True)
     if args.mask_two_level:
         ME.set_mask_sort_two_level(True)
     seg, rot, kp = [m.to(dev) for m in build_models(ME, kp_backbone=args.kp_backbone)]

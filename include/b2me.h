@@ -118,6 +118,11 @@ int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* tab
  */
 int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t* keys, void* ws, size_t ws_bytes,
                         b2me_stream_t stream);
+/* Mask keys with a spatial tie-break: key[row] = mask key << 37 | frame << 30 | Morton code of coords[row] / ts
+ * (coords [V,4] i32 = b,x,y,z; ts a power of two). Rows with the same neighbour pattern follow a space-filling curve,
+ * so the neighbours a tile gathers for its different kernel offsets overlap and are re-read from L2. ws: >= 128 bytes. */
+int b2me_mask_sort_keys_morton(const int32_t* nbr, const int32_t* coords, int64_t V, int K, int ts, int64_t* keys,
+                               void* ws, size_t ws_bytes, b2me_stream_t stream);
 /* Two-level keys (K = 27 maps): the 10 rarest offsets of the map form the most significant part as above, the other
  * offsets are ordered per segment by their frequency among the rows of that segment. Fewer (tile, offset) passes than
  * the one-level keys; same contract otherwise. ws: >= b2me_mask_sort_keys2_ws_bytes(V). */

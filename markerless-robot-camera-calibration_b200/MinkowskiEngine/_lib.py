@@ -30,6 +30,7 @@ SIGNATURES = {
     "b2me_mask_sort_keys": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "b2me_mask_sort_keys2_ws_bytes": (_sz, [_i64]),
     "b2me_mask_sort_keys2": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "b2me_mask_sort_keys_morton": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "b2me_mask_sort_keys64": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "b2me_spconv_fwd_simt": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
                                     _i32, _f32, _vp, _i32, _vp]),

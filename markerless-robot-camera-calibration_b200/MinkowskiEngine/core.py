@@ -45,6 +45,9 @@ class _State:
     # K = 27 maps: per-segment order of the common offsets (b2me_mask_sort_keys2). Off by default: at 32 frames the
     # one-level order already reaches 0.885 row efficiency (two-level 0.901: conv -1 ms, key kernels +5 ms per step)
     mask_sort_two_level = False
+    # k3 maps: Morton order inside a mask group (b2me_mask_sort_keys_morton). Off by default: measured on one box, the
+    # convolution rate does not change (MMA-executed 1053-1060 vs 1058-1068 TFLOP/s) and the 64-bit sort costs ~2 ms
+    mask_sort_morton = False
     compute_dtype = torch.float32
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     profile = None  # bench.py hook, see ops._profile_conv
@@ -76,6 +79,11 @@ def set_mask_sort(flag):
     _State.mask_sort = bool(flag)
 
 
+def set_mask_sort_morton(on):
+    """A/B switch: Morton (True, default) or first-occurrence (False) order inside a mask group of the k3 maps."""
+    _State.mask_sort_morton = bool(on)
+
+
 def set_mask_sort_two_level(on):
     """A/B switch: two-level (True, default) or one-level (False) mask-sort keys for the K = 27 maps."""
     _State.mask_sort_two_level = bool(on)
@@ -86,13 +94,18 @@ def set_mask_sort_block(rows):
     _State.mask_sort_block = int(rows)
 
 
-def mask_sorted_perm(nbr, V, K, block_rows=None):
+def mask_sorted_perm(nbr, V, K, block_rows=None, coords=None, ts=1):
     """row order that groups rows with the same neighbour pattern inside blocks of `block_rows` consecutive rows
     (K3b keys + a device sort)."""
     if block_rows is None:
         block_rows = _State.mask_sort_block
     ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
-    if block_rows == 0 and _State.mask_sort_two_level and K == 27:
+    if block_rows == 0 and coords is not None and _State.mask_sort_morton:
+        # mask keys + Morton tie-break: rows with the same neighbour pattern follow a space-filling curve
+        keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
+        check(lib.b2me_mask_sort_keys_morton(ptr(nbr), ptr(coords), V, K, int(ts), ptr(keys), ptr(ws), ws.numel(),
+                                             stream()), "mask_sort_keys_morton")
+    elif block_rows == 0 and _State.mask_sort_two_level and K == 27:
         # two-level keys: global rarest-first segment + per-segment order of the remaining offsets
         ws = torch.empty((lib.b2me_mask_sort_keys2_ws_bytes(V),), dtype=torch.uint8, device=nbr.device)
         keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
@@ -226,7 +239,8 @@ class CoordinateManager:
         lv = self.levels[key]
         if lv.perm_k3 is None:
             nbr = self.kernel_map_k3(key)
-            perm = mask_sorted_perm(nbr, lv.V, 27) if (_State.mask_sort and lv.V >= _State.mask_sort_min_rows) else None
+            perm = (mask_sorted_perm(nbr, lv.V, 27, coords=lv.coords, ts=key._ts)
+                    if (_State.mask_sort and lv.V >= _State.mask_sort_min_rows) else None)
             lv.perm_k3 = (perm, tile_masks(nbr, perm, lv.V, 27))
         return lv.perm_k3
 

@@ -563,6 +563,66 @@ extern "C" int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t
     return B2ME_OK;
 }
 
+// Mask keys with a spatial tie-break: key = mask key << 37 | frame << 30 | Morton code of the voxel (10 bits per axis
+// of coord / ts, wrapped). Rows with the same neighbour pattern then follow a space-filling curve instead of the
+// first-occurrence (depth-image raster) order, so the rows of a tile - and of the tiles that run concurrently - form
+// compact 3-D patches whose gathered neighbours overlap across kernel offsets: the re-gathers hit L2 instead of DRAM.
+__device__ __forceinline__ unsigned int morton_spread10(unsigned int v) {  // 10 bits -> every third bit
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_mask_keys_morton(const int32_t* __restrict__ nbr, const int4* __restrict__ coords,
+                                                          int64_t V, int K, int ts_shift,
+                                                          const unsigned int* __restrict__ counts,
+                                                          long long* __restrict__ keys) {
+    __shared__ int bitpos[32];
+    if (threadIdx.x < K) {
+        const unsigned int mine = counts[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const unsigned int c = counts[j];
+            if (c < mine || (c == mine && j < (int)threadIdx.x)) ++rank;
+        }
+        bitpos[threadIdx.x] = K - 1 - rank;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    unsigned int key = 0u;
+    for (int k = 0; k < K; ++k)
+        if (__ldg(nbr + v * K + k) >= 0) key |= 1u << bitpos[k];
+    const int4 c = __ldg(coords + v);  // (b, x, y, z)
+    const unsigned int m = morton_spread10((unsigned int)(c.y >> ts_shift)) |
+                           (morton_spread10((unsigned int)(c.z >> ts_shift)) << 1) |
+                           (morton_spread10((unsigned int)(c.w >> ts_shift)) << 2);
+    keys[v] = ((long long)reflect_key(key) << 37) | ((long long)(c.x & 0x7F) << 30) | (long long)m;
+}
+
+extern "C" int b2me_mask_sort_keys_morton(const int32_t* nbr, const int32_t* coords, int64_t V, int K, int ts,
+                                          int64_t* keys, void* ws, size_t ws_bytes, b2me_stream_t stream) {
+    if (!nbr || !coords || !keys || !ws || V < 0 || K < 1 || K > 27 || ts < 1 || (ts & (ts - 1))) return B2ME_EINVAL;
+    if (ws_bytes < 32 * sizeof(unsigned int)) return B2ME_EWORKSPACE;
+    if (V == 0) return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(ws);
+    cudaMemsetAsync(counts, 0, 32 * sizeof(unsigned int), s);
+    const int64_t total = V * K;
+    int64_t blocks = ceil_div64(total, 256 * 8);
+    if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
+    int shift = 0;
+    while ((1 << shift) < ts) ++shift;
+    k_offset_counts<<<(unsigned)blocks, 256, 0, s>>>(nbr, total, K, counts);
+    k_mask_keys_morton<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(nbr, reinterpret_cast<const int4*>(coords), V, K, shift,
+                                                                    counts, reinterpret_cast<long long*>(keys));
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
 // Two-level keys: the T rarest offsets of the map form the segment (most significant part of the key, rarest first,
 // as above); the remaining R = K - T offsets are then ordered PER SEGMENT by their frequency among the rows of that
 // segment (rarest first; offsets that no row or every row of the segment has go last: they cost nothing). The

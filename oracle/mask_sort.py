@@ -66,3 +66,23 @@ def passes(nbr, order, rows_per_tile=256):
     pad = (-V) % rows_per_tile
     pres = np.concatenate((pres, np.zeros((pad, K), bool)))
     return int(pres.reshape(-1, rows_per_tile, K).any(1).sum())
+
+
+def _spread10(v):
+    v = v.astype(np.uint64) & np.uint64(0x3FF)
+    out = np.zeros_like(v)
+    for b in range(10):
+        out |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+    return out
+
+
+def keys_morton(nbr, coords, ts=1):
+    """b2me_mask_sort_keys_morton: reflected mask key << 37 | frame (7 bits) << 30 | 30-bit Morton code of coord / ts
+    (x fastest, 10 wrapped bits per axis), as a signed 64-bit key."""
+    shift = int(ts).bit_length() - 1
+    c = coords.astype(np.int64)
+    m = (_spread10(c[:, 1] >> shift) | (_spread10(c[:, 2] >> shift) << np.uint64(1))
+         | (_spread10(c[:, 3] >> shift) << np.uint64(2)))
+    key = reflect(_global_keys(nbr)).astype(np.uint64)
+    full = (key << np.uint64(37)) | ((c[:, 0].astype(np.uint64) & np.uint64(0x7F)) << np.uint64(30)) | m
+    return full.view(np.int64)

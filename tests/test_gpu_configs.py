@@ -174,8 +174,27 @@ def test_mask_sort_keys_match_definition():
         n = nbr.numpy()
         assert np.array_equal(device_keys(nbr.cuda(), False), MS.keys_one_level(n)), nbr.shape
         assert np.array_equal(device_keys(nbr.cuda(), True), MS.keys_two_level(n)), nbr.shape
+    # Morton tie-break keys (the default order of the k3 maps) on the frame's map, stride 1 and a fake stride 2
+    V = sp.C.shape[0]
+    for ts in (1, 2):
+        k64 = torch.empty(V, dtype=torch.int64, device="cuda")
+        ws = torch.empty(128, dtype=torch.uint8, device="cuda")
+        check(lib.b2me_mask_sort_keys_morton(ptr(frame_nbr.cuda()), ptr(sp.C), V, 27, ts, ptr(k64), ptr(ws), ws.numel(),
+                                             stream()))
+        assert np.array_equal(k64.cpu().numpy(), MS.keys_morton(frame_nbr.numpy(), sp.C.cpu().numpy(), ts)), ts
+    perm = ME.mask_sorted_perm(frame_nbr.cuda(), V, 27, coords=sp.C, ts=1)   # one-level unless the switch is on
+    ME.set_mask_sort_morton(True)
+    try:
+        perm_m = ME.mask_sorted_perm(frame_nbr.cuda(), V, 27, coords=sp.C, ts=1)
+    finally:
+        ME.set_mask_sort_morton(False)
+    for pm in (perm, perm_m):
+        assert torch.equal(torch.sort(pm.long())[0].cpu(), torch.arange(V))
     n = frame_nbr.numpy()
     p_nat = MS.passes(n, np.arange(len(n)))
     p_one = MS.passes(n, np.argsort(MS.keys_one_level(n), kind="stable"))
     p_two = MS.passes(n, np.argsort(MS.keys_two_level(n), kind="stable"))
     assert p_two < p_one < 0.6 * p_nat, (p_nat, p_one, p_two)
+    # the tie-break only reorders rows inside a mask group: same passes as the one-level order, up to group boundaries
+    p_mor = MS.passes(n, np.argsort(MS.keys_morton(n, sp.C.cpu().numpy(), 1), kind="stable"))
+    assert abs(p_mor - p_one) <= 0.05 * p_one, (p_one, p_mor)

@@ -1,8 +1,10 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for mb in 0 131072 65536 262144 0; do
-  echo "== mask-block $mb"
-  timeout 200 python bench.py --frames 32 --steps 3 --warmup 2 --no-cpu-baseline --mask-block $mb 2>&1 | tail -1 | python -c "
+timeout 300 python -m pytest tests/test_gpu_configs.py tests/test_gpu_conv.py -x -q -m gpu > gpurun_out/pytest_morton.log 2>&1; echo "configs+conv rc=$?"
+tail -4 gpurun_out/pytest_morton.log
+for m in "" "--mask-no-morton" "" "--mask-no-morton"; do
+  echo "== bench $m"
+  timeout 200 python bench.py --frames 32 --steps 3 --warmup 2 --no-cpu-baseline $m 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())
 r = d['roofline']

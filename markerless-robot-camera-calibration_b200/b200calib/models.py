@@ -205,7 +205,68 @@ def make_models(ME):
                 out[:, 3:7] = F.normalize(out[:, 3:7], p=2, dim=1)
             return out
 
+    class AliveUNet(MinkUNet):
+        """model/backbone/aliveunet.py:45-275: the seven-level U-Net the reference falls back to when
+        STRUCTURE.backbone names no MinkUNet variant. PLANES = m x (1..7, 7..1) (m = STRUCTURE.m, 32 in
+        config/default.yaml), `block_reps` blocks per stage, BasicBlock or Bottleneck; stride-2 convolutions down to
+        tensor stride 128, transposed convolutions back up, every decoder stage takes the concatenation with the
+        encoder output of its stride. Same attribute names / state-dict keys as the reference class. Its forward
+        returns the last decoder stage (`final` is constructed but not applied, aliveunet.py:264-265)."""
+        ENC = [("conv1p1s2", "bn1", "block1"), ("conv2p2s2", "bn2", "block2"), ("conv3p4s2", "bn3", "block3"),
+               ("conv4p8s2", "bn4", "block4"), ("conv5p16s2", "bn5", "block5"), ("conv6p32s2", "bn6", "block6"),
+               ("conv7p64s2", "bn7", "block7")]
+        DEC = [("convtr7", "bntr7", "block8"), ("convtr8", "bntr8", "block9"), ("convtr9", "bntr9", "block10"),
+               ("convtr10", "bntr10", "block11"), ("convtr11", "bntr11", "block12"), ("convtr12", "bntr12", "block13"),
+               ("convtr13", "bntr13", "block14")]
+
+        def __init__(self, in_channels, out_channels, D=3, m=32, block_reps=1, bottleneck=False):
+            nn.Module.__init__(self)
+            self.BLOCK = blocks["bottleneck" if bottleneck else "basic"]
+            planes = tuple(i * m for i in (list(range(1, 8)) + list(range(7, 0, -1))))
+            self.PLANES, self.LAYERS, self.D = planes, (block_reps,) * len(planes), D
+            exp = self.BLOCK.expansion
+            self.inplanes = INIT_DIM
+            self.conv0p1s1 = ME.MinkowskiConvolution(in_channels, self.inplanes, kernel_size=3, dimension=D)
+            self.bn0 = ME.MinkowskiBatchNorm(self.inplanes)
+            for i, (cname, bname, blk) in enumerate(self.ENC):
+                setattr(self, cname, ME.MinkowskiConvolution(self.inplanes, self.inplanes, kernel_size=2, stride=2,
+                                                             dimension=D))
+                setattr(self, bname, ME.MinkowskiBatchNorm(self.inplanes))
+                setattr(self, blk, self._stage(planes[i], block_reps))
+            # decoder stage j (block 8 + j): transposed conv to planes[7 + j] channels (the reference passes
+            # PLANES[7] for the first and PLANES[8 + j - 1] after it, aliveunet.py:118-168), then the stage on
+            # planes[8 + j] + skip channels; the last stage repeats planes[13] on the stem output
+            tr_out = [planes[7]] + [planes[8 + j] for j in range(6)]
+            stage_p = [planes[8 + j] for j in range(6)] + [planes[13]]
+            # the reference sizes stage j for planes[8 + j] + planes[6 - j] * expansion input channels
+            # (aliveunet.py:123,131,...): equal to what forward concatenates (planes[7 + j] + planes[5 - j] * expansion)
+            # only for BasicBlock - with Bottleneck the reference class constructs but cannot run; mirrored as is
+            skip_ch = [planes[6 - j] * exp for j in range(6)] + [INIT_DIM]
+            for j, (cname, bname, blk) in enumerate(self.DEC):
+                setattr(self, cname, ME.MinkowskiConvolutionTranspose(self.inplanes, tr_out[j], kernel_size=2, stride=2,
+                                                                      dimension=D))
+                setattr(self, bname, ME.MinkowskiBatchNorm(tr_out[j]))
+                self.inplanes = stage_p[j] + skip_ch[j]
+                setattr(self, blk, self._stage(stage_p[j], block_reps))
+            self.final = ME.MinkowskiConvolution(planes[13] * exp, out_channels, kernel_size=1, bias=True, dimension=D)
+            self.relu = ME.MinkowskiReLU(inplace=True)
+            self._init_weights()
+
+        def forward(self, x):
+            out = self.relu(self.bn0(self.conv0p1s1(x)))
+            skips = [out]
+            for i, (cname, bname, blk) in enumerate(self.ENC):
+                out = self.relu(getattr(self, bname)(getattr(self, cname)(out)))
+                out = getattr(self, blk)(out)
+                if i < 6:
+                    skips.append(out)
+            for (cname, bname, blk), skip in zip(self.DEC, reversed(skips)):
+                out = self.relu(getattr(self, bname)(getattr(self, cname)(out)))
+                out = getattr(self, blk)(ME.cat(out, skip))
+            return out
+
     ns = type("Models", (), {})()
+    ns.AliveUNet = AliveUNet
     ns.MinkUNet = MinkUNet
     ns.RobotNetSegmentation = RobotNetSegmentation
     ns.RobotNetVote = RobotNetVote

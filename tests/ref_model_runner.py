@@ -44,9 +44,20 @@ from model.robotnet_segmentation import RobotNetSegmentation as RefSeg  # noqa: 
 from model.robotnet_vote import RobotNetVote as RefVote  # noqa: E402
 from model.robotnet_encode import RobotNetEncode as RefEnc  # noqa: E402
 from model.robotnet import RobotNet as RefRobotNet  # noqa: E402
+from model.backbone.aliveunet import AliveUNet as RefAlive, AliveUNetBase  # noqa: E402  (default.yaml: Bottleneck)
+from MinkowskiEngine.modules.resnet_block import BasicBlock as rb_basic  # noqa: E402
 from b200calib.models import make_models, randomize_bn_stats  # noqa: E402
 
 M = make_models(ME)
+
+
+class RefAliveBasic(AliveUNetBase):
+    """the reference's base class with the BasicBlock configuration (STRUCTURE.bottleneck false, block_reps 1): the
+    Bottleneck configuration of default.yaml constructs but its forward cannot run (channel arithmetic of
+    aliveunet.py:123 only matches the concatenation for expansion 1)."""
+    BLOCK = rb_basic
+    PLANES = tuple(i * 32 for i in (list(range(1, 8)) + list(range(7, 0, -1))))
+    LAYERS = (1,) * 14
 
 
 def same_keys(a, b, name):
@@ -59,7 +70,9 @@ def same_keys(a, b, name):
 pairs = [("segmentation", RefSeg(3, num_classes=3), M.RobotNetSegmentation(3, num_classes=3)),
          ("vote", RefVote(3), M.RobotNetVote(3)),
          ("encode", RefEnc(3, 7), M.RobotNetEncode(3, 7)),
-         ("robotnet", RefRobotNet(3, 7), M.RobotNet(3, 7))]
+         ("robotnet", RefRobotNet(3, 7), M.RobotNet(3, 7)),
+         ("aliveunet-bottleneck", RefAlive(3, 7), M.AliveUNet(3, 7, m=32, block_reps=2, bottleneck=True)),
+         ("aliveunet", RefAliveBasic(3, 7), M.AliveUNet(3, 7, m=32, block_reps=1, bottleneck=False))]
 for name, ref, mine in pairs:
     n = same_keys(ref, mine, name)
     print(f"{name}: {n} state-dict entries identical (keys + shapes)")
@@ -69,6 +82,8 @@ if impl == "oracle":
     pts = torch.rand(6000, 3) * torch.tensor([50.0, 50.0, 4.0])
     feats = torch.rand(6000, 3) - 0.5
     for name, ref, mine in pairs:
+        if name == "aliveunet-bottleneck":
+            continue  # constructs (state dict compared above) but the reference's own forward cannot run
         randomize_bn_stats(ref)
         mine.load_state_dict(ref.state_dict())
         ref.eval(), mine.eval()

@@ -164,3 +164,28 @@ def test_other_minkunet_trunks_parity(nets, variant):
             assert err < tol, (variant, dtype, err)
         finally:
             ME.set_compute_dtype(torch.float32)
+
+
+def test_aliveunet_trunk_parity(nets):
+    """AliveUNet (model/backbone/aliveunet.py:45-275, the fall-back trunk of the robotnet
+    models): seven stride-2 levels down to tensor stride 128 and back, channel counts 32..416 in steps of 32, on the
+    same kernels. The mirror equals the unchanged reference class on the oracle (tests/ref_model_runner.py)."""
+    ME, _, _ = nets
+    torch.manual_seed(17)
+    MO, MC = make_models(OME), make_models(ME)
+    o = randomize_bn_stats(MO.AliveUNet(3, 7, m=32, block_reps=1)).eval()
+    c = MC.AliveUNet(3, 7, m=32, block_reps=1)
+    c.load_state_dict(o.state_dict())
+    c = c.cuda().eval()
+    pts, rgb = zip(_frame(width=128, height=96, seed=23))
+    oo, _ = _run(OME, o, pts, rgb, 100.0)
+    for dtype, tol in ((torch.float32, 1e-3), (torch.bfloat16, 3e-2)):
+        ME.set_compute_dtype(dtype)
+        try:
+            co, _ = _run(ME, c, pts, rgb, 100.0, device="cuda")
+            assert torch.equal(co.C.cpu(), oo.C)
+            err = rel_err(co.F.float().cpu(), oo.F)
+            print(f"AliveUNet {dtype}: features rel err {err:.3e}")
+            assert err < tol, (dtype, err)
+        finally:
+            ME.set_compute_dtype(torch.float32)

@@ -20,7 +20,7 @@ def _run(impl):
 @pytest.mark.reference
 def test_reference_models_run_unchanged_on_oracle_me():
     out = _run("oracle")
-    for name in ("segmentation", "vote", "encode", "robotnet"):
+    for name in ("segmentation", "vote", "encode", "robotnet", "aliveunet"):
         assert f"{name}: unchanged reference model == mirror" in out
 
 

@@ -4,7 +4,7 @@
 // list (256-row tile pair x n-tile) round-robin; each CTA gathers the A rows of its own 128-row tile and loads HALF
 // of every weight tile, the leader CTA issues M = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM
 // holds the accumulator of its own 128 rows. Halving the per-SM weight traffic is what lets the stage ring be deep
-// enough (5 x 40 KB at n_tile = 384) to cover the DRAM latency of the gathered rows.
+// enough (4 x 40 KB at n_tile = 384) to cover the DRAM latency of the gathered rows.
 //
 //   work item     2 x 128 output voxels (rows perm[256 t ..]) x n_tile output channels (n_tile <= 384 TMEM columns)
 //   reduction     items = (kernel offset k with at least one neighbour in the tile) x (64-channel chunk)
@@ -20,16 +20,24 @@
 //                 through shared memory so that residual loads and output stores are 64-byte coalesced segments
 //
 //   warps  0-3    gather producers (stage ring runs on across tiles, so the next tile's rows are in flight while
-//                 the tensor pipe finishes the current one)
-//          4      TMEM alloc + MMA issuer (leader) / stage-full relay to the leader's barrier (peer)
+//                 the tensor pipe finishes the current one); prefetch.global.L2 of the next offset's rows
+//          4      TMEM alloc + MMA issuer (leader) / stage-full relay to the leader's barrier (peer). The issue
+//                 loop is warp-uniform: shfl-broadcast warp index / tile masks / TMEM base, one elect.sync branch
+//                 per item, descriptors as 32-bit low words -> UTCHMMA operands live in uniform registers
 //          5      weight (B) bulk-copy issuer
 //          6-7    kernel-map prefetch: the NEXT tile's 128 x K neighbour rows go global -> registers while the
 //                 current tile runs, then registers -> smem the moment the producers release the buffer
-//          8-11   epilogue (warp w owns TMEM lanes 32 (w-8) ..); overlaps the next tile's gathers
+//          8-15   epilogue (warp w owns TMEM lanes 32 (w % 4) .. and the column half (w - 8) / 4); overlaps the
+//                 next tile's gathers, and its MMAs when two accumulators fit TMEM (n_tile <= 256)
 //
-//   barriers      full[s]  (128 cp.async-completion arrivals + 1 expect_tx)  empty[s]  (tcgen05.commit)
-//                 nbr_full[2] (2 prefetch warps)                     nbr_empty    (4 producer warps)
-//                 kmask_empty[2] (MMA + B issuer)                    tmem_full (commit) / tmem_empty (4 epi warps)
+//   barriers      full[s]  (128 cp.async-completion arrivals + 1 expect_tx + the peer's relay on the leader)
+//                 empty[s] (tcgen05.commit, multicast to both CTAs)
+//                 nbr_full (2 prefetch warps)                        nbr_empty    (4 producer warps)
+//                 tmem_full[2] (commit) / tmem_empty[2] (8 epilogue warps of each CTA, on the leader)
+//
+//   B2ME_TC_TMA=1 operands through the TMA unit instead: tile::gather4 copies of the gathered rows (absent neighbour =
+//                 row -1 = out of bounds = zeros) and 2-D boxes of the packed weights, cta_group::2 with the LEADER's
+//                 stage barrier as completion target - no relay, no proxy fence; same speed, kept opt-in
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
@@ -1329,9 +1337,10 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
 #endif
     p.stages = S;
     // B2ME_TC_TMA=1 routes the operands through the TMA unit (tile::gather4 rows + 2-D weight boxes completing on the
-    // leader's barrier, no relay, no proxy fence). Measured on the same box it is slower than the default cp.async
-    // gather + bulk copy + relay path (K27 384->384: 5.36 vs 4.87 ms; the 32 UTMALDG per item serialise per lane), so
-    // it stays an opt-in alternative that the parity tests also cover.
+    // leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
+    // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms once the 8 UTMALDG per warp and item
+    // issue from uniform registers; whole step 232.2 vs 231.1 ms), so it stays an opt-in alternative that the parity
+    // tests also cover.
     static int want_tma = -1;
     if (want_tma < 0) {
         const char* e = getenv("B2ME_TC_TMA");

@@ -22,13 +22,10 @@ def _need_cuda(t):
 
 
 def square_distance(src, dst):
-    """model/pointnet2_utils.py:22-44 (kept for callers; the kernels below do not build this matrix)."""
-    B, N, _ = src.shape
-    _, M, _ = dst.shape
-    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
-    dist += torch.sum(src ** 2, -1).view(B, N, 1)
-    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
-    return dist
+    """model/pointnet2_utils.py:22-44: all pairwise squared distances [B,N,M] (kept for callers of the module; the
+    kernels below never build this matrix). |s|^2 + |d|^2 - 2 s.d like the reference, so the rounding is the same."""
+    cross = torch.bmm(src, dst.transpose(1, 2))
+    return (-2 * cross + (src * src).sum(-1, keepdim=True)) + (dst * dst).sum(-1).unsqueeze(1)
 
 
 def index_points(points, idx):
@@ -79,135 +76,114 @@ def three_nn(xyz1, xyz2):
     return idx.long(), w
 
 
+def _rows_last(t):
+    """[B, C, N] (the layout the modules exchange) -> [B, N, C] (the layout the primitives take); None stays None."""
+    return None if t is None else t.transpose(1, 2)
+
+
+def _shared_mlp(conv_cls, bn_cls, cin, widths):
+    """(convs, bns): 1x1 convolutions + batch norms of a shared MLP, as two ModuleLists (state-dict keys
+    mlp_convs.i.* / mlp_bns.i.* of the reference modules); created conv, bn, conv, bn, ... like the reference does."""
+    convs, bns = nn.ModuleList(), nn.ModuleList()
+    for cout in widths:
+        convs.append(conv_cls(cin, cout, 1))
+        bns.append(bn_cls(cout))
+        cin = cout
+    return convs, bns
+
+
+def _apply_mlp(x, convs, bns):
+    for conv, bn in zip(convs, bns):
+        x = F.relu(bn(conv(x)))
+    return x
+
+
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
-    """model/pointnet2_utils.py:113-140."""
-    B, N, C = xyz.shape
-    S = npoint
-    fps_idx = farthest_point_sample(xyz, npoint)
-    new_xyz = index_points(xyz, fps_idx)
-    idx = query_ball_point(radius, nsample, xyz, new_xyz)
-    grouped_xyz = index_points(xyz, idx)
-    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
+    """model/pointnet2_utils.py:113-140: FPS centroids, a ball of `nsample` neighbours around each, neighbour
+    coordinates relative to their centroid (+ the neighbours' features). xyz [B,N,3], points [B,N,D] or None ->
+    new_xyz [B,npoint,3], new_points [B,npoint,nsample,3(+D)]."""
+    centroid_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, centroid_idx)
+    ball_idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    ball_xyz = index_points(xyz, ball_idx)
+    new_points = ball_xyz - new_xyz.unsqueeze(2)
     if points is not None:
-        new_points = torch.cat([grouped_xyz_norm, index_points(points, idx)], dim=-1)
-    else:
-        new_points = grouped_xyz_norm
-    if returnfps:
-        return new_xyz, new_points, grouped_xyz, fps_idx
-    return new_xyz, new_points
+        new_points = torch.cat((new_points, index_points(points, ball_idx)), dim=-1)
+    return (new_xyz, new_points, ball_xyz, centroid_idx) if returnfps else (new_xyz, new_points)
 
 
 def sample_and_group_all(xyz, points):
-    """model/pointnet2_utils.py:143-161."""
+    """model/pointnet2_utils.py:143-161: one group holding the whole cloud, centred on the origin."""
     B, N, C = xyz.shape
-    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
-    grouped_xyz = xyz.view(B, 1, N, C)
+    everything = xyz.reshape(B, 1, N, C)
     if points is not None:
-        new_points = torch.cat([grouped_xyz, points.view(B, 1, N, -1)], dim=-1)
-    else:
-        new_points = grouped_xyz
-    return new_xyz, new_points
+        everything = torch.cat((everything, points.reshape(B, 1, N, -1)), dim=-1)
+    return xyz.new_zeros((B, 1, C)), everything
 
 
 class PointNetSetAbstraction(nn.Module):
-    """model/pointnet2_utils.py:164-204 (same attributes -> same state-dict keys)."""
+    """model/pointnet2_utils.py:164-204 (same attributes -> same state-dict keys): sample + group + shared MLP + max
+    over each group. forward(xyz [B,3,N], points [B,D,N] | None) -> (new_xyz [B,3,S], new_points [B,mlp[-1],S])."""
 
     def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
         super().__init__()
-        self.npoint, self.radius, self.nsample = npoint, radius, nsample
-        self.mlp_convs = nn.ModuleList()
-        self.mlp_bns = nn.ModuleList()
-        last_channel = in_channel
-        for out_channel in mlp:
-            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
-            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
-            last_channel = out_channel
-        self.group_all = group_all
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs, self.mlp_bns = _shared_mlp(nn.Conv2d, nn.BatchNorm2d, in_channel, mlp)
 
     def forward(self, xyz, points):
-        xyz = xyz.permute(0, 2, 1)
-        if points is not None:
-            points = points.permute(0, 2, 1)
+        xyz, points = _rows_last(xyz), _rows_last(points)
         if self.group_all:
-            new_xyz, new_points = sample_and_group_all(xyz, points)
+            new_xyz, grouped = sample_and_group_all(xyz, points)
         else:
-            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points)
-        new_points = new_points.permute(0, 3, 2, 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))
-        new_points = torch.max(new_points, 2)[0]
-        return new_xyz.permute(0, 2, 1), new_points
+            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points)
+        feats = _apply_mlp(grouped.permute(0, 3, 2, 1), self.mlp_convs, self.mlp_bns)   # [B, C, nsample, S]
+        return new_xyz.transpose(1, 2), feats.max(dim=2).values
 
 
 class PointNetSetAbstractionMsg(nn.Module):
-    """model/pointnet2_utils.py:207-262."""
+    """model/pointnet2_utils.py:207-262: multi-scale grouping - one ball query + shared MLP per radius around the same
+    FPS centroids, outputs concatenated along the channels."""
 
     def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
         super().__init__()
         self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
-        self.conv_blocks = nn.ModuleList()
-        self.bn_blocks = nn.ModuleList()
-        for mlp in mlp_list:
-            convs, bns = nn.ModuleList(), nn.ModuleList()
-            last_channel = in_channel + 3
-            for out_channel in mlp:
-                convs.append(nn.Conv2d(last_channel, out_channel, 1))
-                bns.append(nn.BatchNorm2d(out_channel))
-                last_channel = out_channel
+        self.conv_blocks, self.bn_blocks = nn.ModuleList(), nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = _shared_mlp(nn.Conv2d, nn.BatchNorm2d, in_channel + 3, widths)
             self.conv_blocks.append(convs)
             self.bn_blocks.append(bns)
 
     def forward(self, xyz, points):
-        xyz = xyz.permute(0, 2, 1)
-        if points is not None:
-            points = points.permute(0, 2, 1)
-        B, N, C = xyz.shape
-        S = self.npoint
-        new_xyz = index_points(xyz, farthest_point_sample(xyz, S))
-        new_points_list = []
-        for i, radius in enumerate(self.radius_list):
-            group_idx = query_ball_point(radius, self.nsample_list[i], xyz, new_xyz)
-            grouped_xyz = index_points(xyz, group_idx) - new_xyz.view(B, S, 1, C)
+        xyz, points = _rows_last(xyz), _rows_last(points)
+        new_xyz = index_points(xyz, farthest_point_sample(xyz, self.npoint))
+        scales = []
+        for radius, nsample, convs, bns in zip(self.radius_list, self.nsample_list, self.conv_blocks, self.bn_blocks):
+            ball_idx = query_ball_point(radius, nsample, xyz, new_xyz)
+            grouped = index_points(xyz, ball_idx) - new_xyz.unsqueeze(2)
             if points is not None:
-                grouped_points = torch.cat([index_points(points, group_idx), grouped_xyz], dim=-1)
-            else:
-                grouped_points = grouped_xyz
-            grouped_points = grouped_points.permute(0, 3, 2, 1)
-            for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
-                grouped_points = F.relu(bn(conv(grouped_points)))
-            new_points_list.append(torch.max(grouped_points, 2)[0])
-        return new_xyz.permute(0, 2, 1), torch.cat(new_points_list, dim=1)
+                grouped = torch.cat((index_points(points, ball_idx), grouped), dim=-1)   # features first, as the reference
+            scales.append(_apply_mlp(grouped.permute(0, 3, 2, 1), convs, bns).max(dim=2).values)
+        return new_xyz.transpose(1, 2), torch.cat(scales, dim=1)
 
 
 class PointNetFeaturePropagation(nn.Module):
-    """model/pointnet2_utils.py:265-318."""
+    """model/pointnet2_utils.py:265-318: features of the coarse level interpolated onto the fine level (inverse
+    distance weights of the three nearest coarse points; a single coarse point is broadcast), concatenated with the
+    fine level's own features, then a shared MLP. forward(xyz1 [B,3,N] fine, xyz2 [B,3,S] coarse, points1 [B,D1,N] |
+    None, points2 [B,D2,S]) -> [B, mlp[-1], N]."""
 
     def __init__(self, in_channel, mlp):
         super().__init__()
-        self.mlp_convs = nn.ModuleList()
-        self.mlp_bns = nn.ModuleList()
-        last_channel = in_channel
-        for out_channel in mlp:
-            self.mlp_convs.append(nn.Conv1d(last_channel, out_channel, 1))
-            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
-            last_channel = out_channel
+        self.mlp_convs, self.mlp_bns = _shared_mlp(nn.Conv1d, nn.BatchNorm1d, in_channel, mlp)
 
     def forward(self, xyz1, xyz2, points1, points2):
-        xyz1 = xyz1.permute(0, 2, 1)
-        xyz2 = xyz2.permute(0, 2, 1)
-        points2 = points2.permute(0, 2, 1)
-        B, N, C = xyz1.shape
-        S = xyz2.shape[1]
-        if S == 1:
-            interpolated_points = points2.repeat(1, N, 1)
+        fine, coarse, coarse_feats = _rows_last(xyz1), _rows_last(xyz2), _rows_last(points2)
+        n_fine = fine.shape[1]
+        if coarse.shape[1] == 1:
+            carried = coarse_feats.repeat(1, n_fine, 1)
         else:
-            idx, weight = three_nn(xyz1, xyz2)
-            interpolated_points = torch.sum(index_points(points2, idx) * weight.view(B, N, 3, 1), dim=2)
+            nn_idx, nn_w = three_nn(fine, coarse)
+            carried = (index_points(coarse_feats, nn_idx) * nn_w.unsqueeze(-1)).sum(dim=2)
         if points1 is not None:
-            new_points = torch.cat([points1.permute(0, 2, 1), interpolated_points], dim=-1)
-        else:
-            new_points = interpolated_points
-        new_points = new_points.permute(0, 2, 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            new_points = F.relu(bn(conv(new_points)))
-        return new_points
+            carried = torch.cat((_rows_last(points1), carried), dim=-1)
+        return _apply_mlp(carried.transpose(1, 2), self.mlp_convs, self.mlp_bns)

@@ -278,7 +278,14 @@ k_linear_small(const void* __restrict__ in, int in_dtype, int64_t V, int Cin, co
 // Vectorised variant for the head (Cin = 1024 bf16 / f32 rows): a warp takes LS_ROWS rows at a time, every lane reads
 // 16 bytes of each row per step (the warp covers 512 contiguous bytes), the weights come from shared memory once per
 // step for all LS_ROWS rows. HBM-bound: V * Cin * e bytes in, V * (4 Cout + 1) out.
+#ifndef LS_ROWS
 #define LS_ROWS 4
+#endif
+#ifndef LS_BLOCKS_PER_SM
+// persistent blocks per SM of the vectorised head linear. Measured on V = 8.9 M rows x 1024 bf16 -> 3 (tools/
+// linear_probe.py, same box): 4 blocks 4.19 ms (4.35 TB/s), 8 blocks 3.40 ms (5.37 TB/s); 8 rows per warp: 4.8 ms
+#define LS_BLOCKS_PER_SM 8
+#endif
 template <int CO, bool BF16>
 __global__ void __launch_bounds__(256)
 k_linear_small_vec(const void* __restrict__ in, int64_t V, int Cin, const float* __restrict__ Wt,
@@ -364,7 +371,7 @@ template <int CO>
 static void launch_linear_small_vec(const void* in, int in_dtype, int64_t V, int Cin, const float* Wt, const float* bias,
                                     float* out_logits, uint8_t* out_argmax, size_t smem, cudaStream_t s) {
     int64_t blocks = ceil_div64(ceil_div64(V, LS_ROWS), 8);
-    if (blocks > B2ME_NUM_SMS * 4) blocks = B2ME_NUM_SMS * 4;
+    if (blocks > B2ME_NUM_SMS * LS_BLOCKS_PER_SM) blocks = B2ME_NUM_SMS * LS_BLOCKS_PER_SM;
     if (in_dtype == B2ME_BF16) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(k_linear_small_vec<CO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -5,7 +5,9 @@
  * Boundary rules:
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
  *   - the caller owns every buffer (inputs, outputs, hash tables, workspaces); the library never
- *     allocates, frees or synchronises; every entry point enqueues on the caller's stream;
+ *     allocates, frees or synchronises; every entry point enqueues on the caller's stream and acts on the
+ *     CURRENT device (the only process-wide state is a cache of per-device constants: SM count, a driver
+ *     function pointer). One host thread per stream; entry points are not re-entrant on one stream;
  *   - return value 0 = success, negative B2ME_E* otherwise (b2me_strerror gives the text);
  *   - data-dependent counts (number of voxels V, ...) are written to device scalars; the caller reads
  *     them back when it needs a host-side shape.
@@ -35,6 +37,8 @@ typedef void* b2me_stream_t; /* cudaStream_t */
 /* dtypes */
 #define B2ME_F32 0
 #define B2ME_BF16 1
+#define B2ME_TF32 2 /* fp32 storage holding tf32-representable values (10-bit mantissa, rounded to nearest): the
+                       operand / output type of the tf32 tensor-core mode */
 
 /* activations fused in epilogues */
 #define B2ME_ACT_NONE 0
@@ -152,27 +156,51 @@ int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, int Cin2, i
                          const void* residual, int res_dtype, int act, float slope,
                          void* out, int out_dtype, b2me_stream_t stream);
 
-/* tcgen05 path: bf16 operands, fp32 accumulation in TMEM.  Weights must be pre-packed. */
-size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout);
+/* tcgen05 path: bf16 (B2ME_BF16) or tf32 (B2ME_TF32: fp32 rows holding tf32-representable values) operands, fp32
+ * accumulation in TMEM.  Weights must be pre-packed for the same operand type. */
+size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout, int op_dtype);
 int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout);
-int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, void* packed,
+int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, int op_dtype, void* packed,
                          b2me_stream_t stream);
 /* perm [V_out] i32 (may be null = identity): tile t computes the output rows perm[128 t .. 128 t + 127]; any
  * permutation gives bit-identical results (absent neighbours contribute exact zeros), a mask-sorted one
- * (b2me_mask_sort_keys64) lets tiles skip the kernel offsets none of their rows has.
+ * (b2me_mask_sort_keys) lets tiles skip the kernel offsets none of their rows has.
  * tile_masks [ceil(V_out / 256)] u32 (required when nbr is given): bit k set when any of the rows
  * perm[256 t .. 256 t + 255] has neighbour k; computed once per (nbr, perm) by b2me_tc_tile_masks and shared by
  * every convolution on that kernel map. */
 int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, int K, uint32_t* masks,
                        b2me_stream_t stream);
-/* V_in: rows of in1 (and of in2, which lies on the same coordinate map); the gathered rows are fetched through TMA
- * tensor maps built per call (tile::gather4: row indices outside [0, V_in) read as zeros). */
-int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in,
+
+/* flags of the tcgen05 entry points */
+#define B2ME_TC_FLAG_TMA 1        /* operands through the TMA unit (cp.async.bulk.tensor tile::gather4 rows + 2-D weight
+                                     boxes) instead of cp.async gathers + cp.async.bulk; same results bit for bit */
+#define B2ME_TC_FLAG_NO_ROT128 2  /* 384-column tiles: one 384-column accumulator (round-1 layout) instead of the early
+                                     release of the 256-column part + alternating 128-column regions; same results */
+
+/* V_in: rows of in1 (and of in2, which lies on the same coordinate map; with B2ME_TC_FLAG_TMA row indices outside
+ * [0, V_in) read as zeros). op_dtype: type of in1 / in2 / packed_w (B2ME_BF16 | B2ME_TF32); residual rows are bf16
+ * for bf16 operands and f32 for tf32 operands. out_dtype: B2ME_BF16 | B2ME_F32 (bf16 operands), B2ME_TF32 | B2ME_F32
+ * (tf32 operands; B2ME_TF32 rounds the stored f32 values to tf32 so that they can feed the next tf32 layer). */
+int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in, int op_dtype,
                        const void* packed_w, const int32_t* nbr, const int32_t* perm,
                        const uint32_t* tile_masks, int K,
                        int64_t V_out, int Cout, const float* scale, const float* shift,
                        const void* residual, int act, float slope,
-                       void* out, int out_dtype, b2me_stream_t stream);
+                       void* out, int out_dtype, int flags, b2me_stream_t stream);
+
+/* Fused head of RobotNetSegmentation / RobotNetVote (model/robotnet_segmentation.py:43-49,
+ * model/robotnet_vote.py:50-56): MinkowskiLinear(Cin, Chid) -> activation -> MinkowskiLinear(Chid, C2) in ONE launch;
+ * the [V, Chid] hidden activation stays on chip.
+ *     hid = act1((in @ W1) * scale1 + shift1)          (tcgen05, W1 packed with b2me_tc_pack_weights(K = 1))
+ *     out_logits[v, :] = hid[v, :] @ W2 + b2           (epilogue FMAs, fp32; bf16 operands: hid is rounded to bf16
+ *                                                       first, exactly like the stored tensor of the unfused path)
+ *     out_argmax[v] = lowest index of the row maximum (utils/output.py:67-73), may be null
+ * W2p [Chid, C2p] f32 with C2p = 4 ceil(C2 / 4), columns >= C2 zero; b2 [C2] or null; C2 <= 16; the output tile of
+ * Chid must be a multiple of 64 columns (Chid = 1024 -> 256). */
+int b2me_head_fused_tc(const void* in, int Cin, int64_t V, int op_dtype, const void* packed_w1, int Chid,
+                       const float* scale1, const float* shift1, int act1, float slope1,
+                       const float* W2p, const float* b2, int C2, float* out_logits, uint8_t* out_argmax,
+                       int flags, b2me_stream_t stream);
 
 /* stand-alone per-channel affine + residual + activation (BatchNorm/ReLU that could not be folded) */
 int b2me_affine_act(const void* in, int in_dtype, int64_t V, int C, const float* scale,
@@ -223,6 +251,17 @@ int b2me_translation_magic(const float* points_xyz, const int32_t* seg_offsets, 
                            const float* quat_wxyz, float x_offset, double* out_pos,
                            b2me_stream_t stream);
 
+/* InferenceEngine.check_sanity (app/inference_engine.py:246-279) with get_6_key_points (utils/data.py:255-335) and
+ * compute_kp_error (utils/metrics.py:130-136), batched over EE crops: confident[s] = 0 when the crop has fewer than
+ * min_points points, when an EE corner is not within 0.04 m of where the pose puts it, or when the mean distance of
+ * the predicted key points (class k of crop s counts when kp_prob[s,k] > kp_threshold; kp_xyz[s,k] = its coordinates)
+ * to the corners / gripper tips found on the crop exceeds kp_margin. points_xyz [n,3] f32, seg_offsets [S+1] i32,
+ * ee_pose [S,7] f64 (x y z qw qx qy qz, the pose BEFORE the ICP refinement), kp_prob [S,K] f32, kp_xyz [S,K,3] f32
+ * (K <= 6; both may be null with K = 0). */
+int b2me_sanity_check(const float* points_xyz, const int32_t* seg_offsets, int S, const double* ee_pose,
+                      const float* kp_prob, const float* kp_xyz, int K, float kp_threshold, int min_points,
+                      double kp_margin, uint8_t* out_confident, b2me_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K7: ClusterUtil.get_largest_cluster (utils/output.py:13-28; sklearn single linkage, 0.06 m) batched:
  * connected components of the graph {d(i,j) < dist} inside every segment; mask[i] = 1 for the points
@@ -230,7 +269,9 @@ int b2me_translation_magic(const float* points_xyz, const int32_t* seg_offsets, 
  * ---------------------------------------------------------------------------------------------- */
 size_t b2me_cluster_workspace_bytes(int64_t n, int S);
 int b2me_largest_cluster(const float* points_xyz, const int32_t* seg_offsets, int S, int64_t n,
-                         double dist, uint8_t* out_mask, int32_t* out_sizes /* [S] largest size */,
+                         double dist, uint8_t* out_mask,
+                         int32_t* out_sizes /* [S] largest size; -1 everywhere when a point was non-finite or outside
+                                               the cell key range (the masks are then not meaningful) */,
                          void* ws, size_t ws_bytes, b2me_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -268,6 +309,13 @@ size_t b2me_ingest_workspace_bytes(int64_t n);
 int b2me_ingest_clouds(const float* xyzrgb, int64_t n, const int32_t* frame_offsets, int F, const float* roi6,
                        float* out_xyz, float* out_rgb, float* out_bidx, int32_t* out_src, int32_t* out_offsets,
                        void* ws, size_t ws_bytes, b2me_stream_t stream);
+
+/* normalize_colors (utils/preprocess.py:20-37) applied per frame of a batch on the device: rgb [n,3] f32 -> out [n,3]
+ * (may alias rgb): / 255 when the frame's maximum exceeds 2, per-channel min-max rescale when the frame has a negative
+ * value, - 0.5 when the result lies in [0, 1]. bidx [n] f32 frame index of every point, frame_offsets [F+1] i32 (device)
+ * rows of every frame, ws: F * 24 bytes. */
+int b2me_normalize_colors(const float* rgb, const float* bidx, int64_t n, const int32_t* frame_offsets, int F,
+                          float* out, void* ws, size_t ws_bytes, b2me_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PointNet++ primitives of the default key-point network (model/pointnet2.py:9-43 through

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2ME_LIB_PATH: developer override used by tools/conv_probe.py to load an instrumented build (lib_debug/)
 LIB_PATH = os.environ.get("B2ME_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libb2me.so")
 
-F32, BF16 = 0, 1
+F32, BF16, TF32 = 0, 1, 2
+TC_FLAG_TMA, TC_FLAG_NO_ROT128 = 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 _vp, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
@@ -34,12 +35,14 @@ SIGNATURES = {
     "b2me_mask_sort_keys64": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "b2me_spconv_fwd_simt": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
                                     _i32, _f32, _vp, _i32, _vp]),
-    "b2me_tc_packed_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "b2me_tc_packed_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "b2me_tc_supported": (_i32, [_i32, _i32, _i32, _i32]),
-    "b2me_tc_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b2me_tc_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2me_tc_tile_masks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
-    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
-                                  _f32, _vp, _i32, _vp]),
+    "b2me_spconv_fwd_tc": (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp,
+                                  _i32, _f32, _vp, _i32, _i32, _vp]),
+    "b2me_head_fused_tc": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _f32, _vp, _vp, _i32, _vp, _vp, _i32,
+                                  _vp]),
     "b2me_affine_act": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "b2me_convert": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "b2me_linear_small": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -49,11 +52,13 @@ SIGNATURES = {
     "b2me_keypoint_reduce": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "b2me_vote_center": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2me_translation_magic": (_i32, [_vp, _vp, _i32, _vp, _f32, _vp, _vp]),
+    "b2me_sanity_check": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _f64, _vp, _vp]),
     "b2me_cluster_workspace_bytes": (_sz, [_i64, _i32]),
     "b2me_largest_cluster": (_i32, [_vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp, _sz, _vp]),
     "b2me_kabsch_batched": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2me_ingest_workspace_bytes": (_sz, [_i64]),
     "b2me_ingest_clouds": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2me_normalize_colors": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
     "b2me_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b2me_ball_query": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
     "b2me_three_nn": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),

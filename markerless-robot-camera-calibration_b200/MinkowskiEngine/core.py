@@ -49,20 +49,60 @@ class _State:
     # convolution rate does not change (MMA-executed 1053-1060 vs 1058-1068 TFLOP/s) and the 64-bit sort costs ~2 ms
     mask_sort_morton = False
     compute_dtype = torch.float32
+    # "bf16" activations on tcgen05 | "tf32": fp32 activations holding tf32 values on tcgen05 kind::tf32 | "f32": SIMT
+    compute_mode = "f32"
+    tc_flags = 0  # B2ME_TC_FLAG_* passed to every tcgen05 launch (operand path, accumulator layout)
+    fuse_head = True  # MinkowskiLinear(.., hidden) -> act -> MinkowskiLinear(hidden, C <= 16) as ONE launch
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     profile = None  # bench.py hook, see ops._profile_conv
 
 
 def set_compute_dtype(dtype):
-    """torch.float32: exact-fp32 SIMT convolutions. torch.bfloat16: bf16 activations, tcgen05 convolutions
-    with fp32 accumulation (BASELINE.json config 2)."""
-    if dtype not in (torch.float32, torch.bfloat16):
-        raise ValueError("compute dtype must be torch.float32 or torch.bfloat16")
-    _State.compute_dtype = dtype
+    """torch.float32 / "f32": exact-fp32 SIMT convolutions.
+    torch.bfloat16 / "bf16": bf16 activations, tcgen05 convolutions with fp32 accumulation (BASELINE.json config 2).
+    "tf32": fp32 activations, tcgen05 kind::tf32 convolutions with fp32 accumulation: the tensor-core mode that
+    meets the 1e-3 fp32 tolerance (activations and weights are rounded to tf32, 10-bit mantissa, to nearest)."""
+    if dtype in (torch.float32, "f32", "fp32", "float32"):
+        _State.compute_dtype, _State.compute_mode = torch.float32, "f32"
+    elif dtype in (torch.bfloat16, "bf16", "bfloat16"):
+        _State.compute_dtype, _State.compute_mode = torch.bfloat16, "bf16"
+    elif dtype in ("tf32", "tfloat32"):
+        _State.compute_dtype, _State.compute_mode = torch.float32, "tf32"
+    else:
+        raise ValueError("compute dtype must be torch.float32, torch.bfloat16 or 'tf32'")
 
 
 def get_compute_dtype():
     return _State.compute_dtype
+
+
+def get_compute_mode():
+    """'f32' | 'bf16' | 'tf32'."""
+    return _State.compute_mode
+
+
+def set_tc_operand_path(path):
+    """how the tcgen05 convolution fetches its operands: "cpasync" (default: 16-byte cp.async gathers + cp.async.bulk
+    weights) or "tma" (cp.async.bulk.tensor tile::gather4 rows + 2-D weight boxes). Bit-identical results."""
+    if path not in ("cpasync", "tma"):
+        raise ValueError('operand path must be "cpasync" or "tma"')
+    _State.tc_flags = (_State.tc_flags & ~_lib.TC_FLAG_TMA) | (_lib.TC_FLAG_TMA if path == "tma" else 0)
+
+
+def get_tc_operand_path():
+    return "tma" if _State.tc_flags & _lib.TC_FLAG_TMA else "cpasync"
+
+
+def set_tc_rot128(on):
+    """384-column tiles: early release of the 256-column accumulator part + alternating 128-column regions (True,
+    default) or the single 384-column accumulator of round 1 (False). Bit-identical results."""
+    _State.tc_flags = (_State.tc_flags & ~_lib.TC_FLAG_NO_ROT128) | (0 if on else _lib.TC_FLAG_NO_ROT128)
+
+
+def set_fuse_head(on):
+    """fused 256 -> 1024 -> C head in one launch (True, default) or the two-launch path with the hidden activation in
+    HBM (False; A/B and parity tests)."""
+    _State.fuse_head = bool(on)
 
 
 def reset_launch_count():
@@ -80,12 +120,12 @@ def set_mask_sort(flag):
 
 
 def set_mask_sort_morton(on):
-    """A/B switch: Morton (True, default) or first-occurrence (False) order inside a mask group of the k3 maps."""
+    """A/B switch: Morton (True) or first-occurrence (False, default) order inside a mask group of the k3 maps."""
     _State.mask_sort_morton = bool(on)
 
 
 def set_mask_sort_two_level(on):
-    """A/B switch: two-level (True, default) or one-level (False) mask-sort keys for the K = 27 maps."""
+    """A/B switch: two-level (True) or one-level (False, default) mask-sort keys for the K = 27 maps."""
     _State.mask_sort_two_level = bool(on)
 
 

@@ -56,18 +56,35 @@ def _weight_f32(module):
     return w3
 
 
-def _weight_packed(module, K, Cin1, Cin2, Cout):
+def _weight_packed(module, K, Cin1, Cin2, Cout, op_code):
+    """SWIZZLE_128B smem image of the weights for the tcgen05 kernel (bf16 or tf32 operands), cached per module."""
     w3 = _weight_f32(module)
-    ver = (w3.data_ptr(), K, Cin1, Cin2, Cout)
+    ver = (w3.data_ptr(), K, Cin1, Cin2, Cout, op_code)
     cache = getattr(module, "_b2me_packed", None)
     if cache is not None and cache[0] == ver and cache[2] is w3:
         return cache[1]
-    nbytes = lib.b2me_tc_packed_bytes(K, Cin1, Cin2, Cout)
+    nbytes = lib.b2me_tc_packed_bytes(K, Cin1, Cin2, Cout, op_code)
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=w3.device)
-    check(lib.b2me_tc_pack_weights(ptr(w3), K, Cin1, Cin2, Cout, ptr(packed), stream()), "tc_pack_weights")
+    check(lib.b2me_tc_pack_weights(ptr(w3), K, Cin1, Cin2, Cout, op_code, ptr(packed), stream()), "tc_pack_weights")
     _count(1)
     module._b2me_packed = (ver, packed, w3)
     return packed
+
+
+def _head_weights(lin):
+    """second linear of a fused head: ([Chid, C2p] f32 zero-padded transpose of nn.Linear.weight, bias), cached."""
+    ver = (_tensor_version(lin.weight), _tensor_version(lin.bias) if lin.bias is not None else None)
+    cached = getattr(lin, "_b2me_head", None)
+    if cached is not None and cached[0] == ver:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        C2, Chid = lin.weight.shape
+        C2p = (C2 + 3) // 4 * 4
+        w = torch.zeros((Chid, C2p), dtype=torch.float32, device=lin.weight.device)
+        w[:, :C2] = lin.weight.detach().float().t()
+        b = lin.bias.detach().float().contiguous() if lin.bias is not None else None
+    lin._b2me_head = (ver, w.contiguous(), b)
+    return lin._b2me_head[1], b
 
 
 # ------------------------------------------------------------------------------------------------ execution
@@ -92,7 +109,7 @@ def _run_elt(p):
     return out
 
 
-def _profile_conv(kind, p, Cin, masks=None):
+def _profile_conv(kind, p, Cin, masks=None, extra=None):
     """bench.py hook: 'census' records the algorithmic work of every convolution launch (pairs = sum_k P_k) and, for
     the tcgen05 kernel, the (256-row tile pair, offset) passes it executes (zero-filled rows included),
     'events' brackets the launch with CUDA events on the launching stream."""
@@ -109,12 +126,24 @@ def _profile_conv(kind, p, Cin, masks=None):
                 rec["passes"] = int(sum(int(((m >> k) & 1).sum().item()) for k in range(p.K)))
             else:
                 rec["passes"] = tiles * p.K
+        if extra:
+            rec.update(extra)
         prof["records"].append(rec)
         return None
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
     prof["records"].append(ev)
     return ev
+
+
+def _tc_mode():
+    """(torch dtype of the activations, operand dtype code, output dtype code) of the tcgen05 path, or None."""
+    mode = _State.compute_mode
+    if mode == "bf16":
+        return torch.bfloat16, _lib.BF16, _lib.BF16
+    if mode == "tf32":
+        return torch.float32, _lib.TF32, _lib.TF32
+    return None
 
 
 def _run_conv(p):
@@ -125,42 +154,86 @@ def _run_conv(p):
     Cin2 = f2.shape[1] if f2 is not None else 0
     K, V_out, Cout = p.K, p.V_out, p.Cout
     dev = f1.device
-    cdt = _State.compute_dtype
     res = p.residual._materialize() if p.residual is not None else None
     small_out = p.extra.get("f32_out", False)
-    use_tc = (cdt == torch.bfloat16 and not small_out and lib.b2me_tc_supported(K, Cin1, Cin2, Cout) == 1)
+    tc = _tc_mode()
+    use_tc = (tc is not None and not small_out and lib.b2me_tc_supported(K, Cin1, Cin2, Cout) == 1)
     if use_tc:
-        f1 = _as_dtype(f1, torch.bfloat16)
+        adt, op_code, out_code = tc
+        f1 = _as_dtype(f1, adt)
         if f2 is not None:
-            f2 = _as_dtype(f2, torch.bfloat16)
+            f2 = _as_dtype(f2, adt)
         if res is not None:
-            res = _as_dtype(res, torch.bfloat16)
-        packed = _weight_packed(p.module, K, Cin1, Cin2, Cout)
-        out = torch.empty((V_out, Cout), dtype=torch.bfloat16, device=dev)
+            res = _as_dtype(res, adt)
+        packed = _weight_packed(p.module, K, Cin1, Cin2, Cout, op_code)
+        out = torch.empty((V_out, Cout), dtype=adt, device=dev)
         perm, masks = p.perm() if p.perm is not None else (None, None)
         ev = _profile_conv("tc", p, Cin1 + Cin2, masks)
-        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, f1.shape[0], ptr(packed), ptr(p.nbr), ptr(perm), ptr(masks), K,
-                                     V_out, Cout, ptr(p.scale), ptr(p.shift), ptr(res), p.act, p.slope, ptr(out),
-                                     _lib.BF16, stream()), "spconv_fwd_tc")
+        check(lib.b2me_spconv_fwd_tc(ptr(f1), Cin1, ptr(f2), Cin2, f1.shape[0], op_code, ptr(packed), ptr(p.nbr),
+                                     ptr(perm), ptr(masks), K, V_out, Cout, ptr(p.scale), ptr(p.shift), ptr(res),
+                                     p.act, p.slope, ptr(out), out_code, _State.tc_flags, stream()), "spconv_fwd_tc")
         if ev is not None:
             ev[1].record()
         _count(1)
         return out
-    # SIMT fp32-accumulate path
+    # SIMT fp32-accumulate path (exact fp32 mode; shapes the tensor-core kernel does not take, e.g. the Cin = 3 stem)
     if f2 is not None and f2.dtype != f1.dtype:
         f2 = _as_dtype(f2, f1.dtype)
     W = _weight_f32(p.module)
-    out_dtype = torch.float32 if (small_out or cdt == torch.float32) else torch.bfloat16
+    mode = _State.compute_mode
+    if small_out or mode == "f32":
+        out_dtype, out_code = torch.float32, _lib.F32
+    elif mode == "tf32":
+        out_dtype, out_code = torch.float32, _lib.TF32  # feeds tf32 tensor-core layers: stored rounded to tf32
+    else:
+        out_dtype, out_code = torch.bfloat16, _lib.BF16
     out = torch.empty((V_out, Cout), dtype=out_dtype, device=dev)
     ev = _profile_conv("simt", p, Cin1 + Cin2)
     check(lib.b2me_spconv_fwd_simt(ptr(f1), Cin1, ptr(f2), Cin2, dtype_code(f1.dtype), ptr(W), ptr(p.nbr), K, V_out,
                                    Cout, ptr(p.scale), ptr(p.shift), ptr(res),
                                    dtype_code(res.dtype) if res is not None else 0, p.act, p.slope, ptr(out),
-                                   dtype_code(out_dtype), stream()), "spconv_fwd_simt")
+                                   out_code, stream()), "spconv_fwd_simt")
     if ev is not None:
         ev[1].record()
     _count(1)
     return out
+
+
+def _try_fused_head(module, x):
+    """MinkowskiLinear(Cin, Chid) -> activation -> this MinkowskiLinear(Chid, C2 <= 16) as one launch
+    (b2me_head_fused_tc): x must still be the pending first linear. Returns the logits SparseTensor or None."""
+    p = x._pending
+    tc = _tc_mode()
+    if (not _State.fuse_head or tc is None or x._F is not None or p is None or p.kind != "conv" or p.K != 1
+            or p.nbr is not None or len(p.src) != 1 or p.residual is not None or p.extra.get("f32_out")
+            or not hasattr(p.module, "linear")):
+        return None
+    lin2 = module.linear
+    Chid, C2 = p.Cout, lin2.out_features
+    f = p.src[0]._materialize()
+    Cin = f.shape[1]
+    if lin2.in_features != Chid or C2 > 16 or lib.b2me_tc_supported(1, Cin, 0, Chid) != 1:
+        return None
+    n_tile = Chid if Chid <= 256 else (256 if Chid % 256 == 0 else (192 if Chid % 192 == 0 else 128))
+    if n_tile % 64 or Chid % n_tile:
+        return None
+    adt, op_code, _ = tc
+    f = _as_dtype(f, adt)
+    V = f.shape[0]
+    packed = _weight_packed(p.module, 1, Cin, 0, Chid, op_code)
+    W2p, b2 = _head_weights(lin2)
+    logits = torch.empty((V, C2), dtype=torch.float32, device=f.device)
+    amax = torch.empty((max(V, 1),), dtype=torch.uint8, device=f.device)
+    ev = _profile_conv("tc", p, Cin, None, dict(fused_head=C2))
+    check(lib.b2me_head_fused_tc(ptr(f), Cin, V, op_code, ptr(packed), Chid, ptr(p.scale), ptr(p.shift), p.act, p.slope,
+                                 ptr(W2p), ptr(b2), C2, ptr(logits), ptr(amax), _State.tc_flags, stream()),
+          "head_fused_tc")
+    if ev is not None:
+        ev[1].record()
+    _count(1)
+    res = x._child(features=logits)
+    res._row_argmax = amax[:V]
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ op builders
@@ -210,6 +283,9 @@ def linear_forward(module, x: SparseTensor):
     lin = module.linear
     Cout = lin.out_features
     if Cout <= 16:
+        fused = _try_fused_head(module, x)
+        if fused is not None:
+            return fused
         # K5: small-N head, fp32 logits straight from the (bf16 or f32) voxel features
         F = x._materialize()
         V = F.shape[0]

@@ -21,7 +21,10 @@ def read_pcd_xyz(path):
     with open(path, "rb") as fp:
         header = {}
         while True:
-            line = fp.readline().decode("ascii", "replace").strip()
+            raw_line = fp.readline()
+            if raw_line == b"":   # EOF before the DATA line: truncated or not a PCD file
+                raise ValueError(f"{path}: no DATA line (truncated or not a PCD file)")
+            line = raw_line.decode("ascii", "replace").strip()
             if not line or line.startswith("#"):
                 continue
             k, *v = line.split()
@@ -117,7 +120,7 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
     check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
                                    ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")
-    _count(2 + int(max_iter))  # grid build + (max_iter + 1) evaluation launches
+    _count(2)  # grid build + ONE persistent cluster launch for all evaluations
     return out_T.view(F, 4, 4), stats
 
 

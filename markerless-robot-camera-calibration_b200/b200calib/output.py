@@ -119,3 +119,42 @@ def translation_magic_batched(points, seg_offsets, quats_wxyz, x_offset=-0.015):
           "translation_magic")
     _count(1)
     return out
+
+
+def sanity_check_batched(points, seg_offsets, ee_poses, kp_prob=None, kp_xyz=None, kp_threshold=0.75,
+                         min_num_of_ee_points=2048, kp_error_margin=0.05):
+    """InferenceEngine.check_sanity (app/inference_engine.py:246-279) for S EE crops on the device -> [S] uint8.
+    points [n,3] f32 (the crops, concatenated), seg_offsets [S+1], ee_poses [S,7] f64 x,y,z,qw,qx,qy,qz (before the ICP
+    refinement), kp_prob [S,K] f32 / kp_xyz [S,K,3] f32: the per-class best key-point probabilities and coordinates
+    (a class counts when its probability exceeds kp_threshold)."""
+    points = points.to(torch.float32).contiguous()
+    dev = points.device
+    offs = _offsets(seg_offsets, dev)
+    S = offs.numel() - 1
+    poses = ee_poses.to(dev, torch.float64).contiguous()
+    K = 0
+    if kp_prob is not None:
+        kp_prob = kp_prob.to(dev, torch.float32).contiguous()
+        kp_xyz = kp_xyz.to(dev, torch.float32).contiguous()
+        K = kp_prob.shape[1]
+    out = torch.zeros((max(S, 1),), dtype=torch.uint8, device=dev)
+    check(lib.b2me_sanity_check(ptr(points), ptr(offs), S, ptr(poses), ptr(kp_prob), ptr(kp_xyz), K, float(kp_threshold),
+                                int(min_num_of_ee_points), float(kp_error_margin), ptr(out), stream()), "sanity_check")
+    _count(1)
+    return out[:S]
+
+
+def normalize_colors_batched(rgb, bidx, frame_offsets):
+    """utils/preprocess.py:20-37 per frame of a batch on the device (no host round trip): rgb [n,3] f32, bidx [n] f32
+    frame index, frame_offsets [F+1] -> [n,3] f32."""
+    rgb = rgb.to(torch.float32).contiguous()
+    dev = rgb.device
+    n = rgb.shape[0]
+    offs = _offsets(frame_offsets, dev)
+    F = offs.numel() - 1
+    out = torch.empty_like(rgb)
+    ws = torch.empty((max(F, 1) * 24,), dtype=torch.uint8, device=dev)
+    check(lib.b2me_normalize_colors(ptr(rgb), ptr(bidx.contiguous()), n, ptr(offs), F, ptr(out), ptr(ws), ws.numel(),
+                                    stream()), "normalize_colors")
+    _count(3)
+    return out

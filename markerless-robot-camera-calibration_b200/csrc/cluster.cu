@@ -85,9 +85,12 @@ __global__ void k_cluster_cells(const float* __restrict__ pts, const int32_t* __
     if (i >= n) return;
     const int seg = seg_of_row(seg_offsets, S, (int)i);
     const double cs = dist * CLUSTER_CELL_FRAC;
-    const int cx = (int)floor((double)pts[i * 3 + 0] / cs);
-    const int cy = (int)floor((double)pts[i * 3 + 1] / cs);
-    const int cz = (int)floor((double)pts[i * 3 + 2] / cs);
+    const double fx = floor((double)pts[i * 3 + 0] / cs), fy = floor((double)pts[i * 3 + 1] / cs),
+                 fz = floor((double)pts[i * 3 + 2] / cs);
+    // a non-finite or far-away point gets a cell outside the key range: b2me_quantize_unique then raises its error flag
+    // (reported through out_sizes = -1) instead of the point silently landing in cell 0
+    const bool ok = isfinite(fx) && isfinite(fy) && isfinite(fz) && fabs(fx) < 1e9 && fabs(fy) < 1e9 && fabs(fz) < 1e9;
+    const int cx = ok ? (int)fx : 0x7fffffff, cy = ok ? (int)fy : 0, cz = ok ? (int)fz : 0;
     cellq[i] = make_int4(seg, cx, cy, cz);
     parent[i] = (int32_t)i;
     comp_size[i] = 0;
@@ -168,7 +171,12 @@ k_cluster_inter(const float* __restrict__ pts, const int32_t* __restrict__ cell_
         if (b == 0xFFFFFFFFu) continue;
         const int a0 = cell_start[a], a1 = cell_start[a + 1], b0 = cell_start[b], b1 = cell_start[b + 1];
         const int repa = sorted[a0], repb = sorted[b0];
-        if (uf_find(parent, repa) == uf_find(parent, repb)) continue;  // warp-uniform
+        // lane 0 alone walks (and path-halves) the forest that other warps are mutating; its verdict is broadcast, so
+        // the skip below is warp-uniform by construction and every lane reaches the full-mask votes that follow
+        int same = 0;
+        if (lane == 0) same = uf_find(parent, repa) == uf_find(parent, repb);
+        same = __shfl_sync(0xffffffffu, same, 0);
+        if (same) continue;
         bool linked = false;
         for (int ia = a0; ia < a1 && !linked; ++ia) {
             const int i = sorted[ia];
@@ -227,10 +235,12 @@ __global__ void k_cluster_best(const int32_t* __restrict__ comp_size, const int3
 }
 
 __global__ void k_cluster_mask(const int32_t* __restrict__ root, const int32_t* __restrict__ seg_offsets, int S,
-                               int64_t n, const unsigned long long* __restrict__ best, uint8_t* __restrict__ mask,
+                               int64_t n, const unsigned long long* __restrict__ best,
+                               const int32_t* __restrict__ counts, uint8_t* __restrict__ mask,
                                int32_t* __restrict__ sizes) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < S && sizes) sizes[i] = (int32_t)(best[i] >> 32);
+    // counts[1] != 0: a point was non-finite / outside the cell key range -> every size reads -1 (error)
+    if (i < S && sizes) sizes[i] = counts[1] ? -1 : (int32_t)(best[i] >> 32);
     if (i >= n) return;
     const int seg = seg_of_row(seg_offsets, S, (int)i);
     const unsigned long long b = best[seg];
@@ -247,6 +257,7 @@ extern "C" int b2me_largest_cluster(const float* points_xyz, const int32_t* seg_
     if (ws_bytes < w.total) return B2ME_EWORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     cudaMemsetAsync(w.best, 0, (size_t)S * 8, s);
+    cudaMemsetAsync(w.counts, 0, 2 * sizeof(int32_t), s);
     const int T = 256;
     const unsigned G = (unsigned)ceil_div64(n > 0 ? n : 1, T);
     if (n > 0) {
@@ -273,7 +284,7 @@ extern "C" int b2me_largest_cluster(const float* points_xyz, const int32_t* seg_
         k_cluster_best<<<G, T, 0, s>>>(w.comp_size, seg_offsets, S, n, w.best);
     }
     const unsigned G2 = (unsigned)ceil_div64((n > S ? n : S), T);
-    k_cluster_mask<<<G2, T, 0, s>>>(w.cursor, seg_offsets, S, n, w.best, out_mask, out_sizes);
+    k_cluster_mask<<<G2, T, 0, s>>>(w.cursor, seg_offsets, S, n, w.best, w.counts, out_mask, out_sizes);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -79,13 +79,20 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
+// round to nearest tf32 (10-bit mantissa), returned in an fp32 container
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t i) {
     return dtype == B2ME_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
                               : reinterpret_cast<const float*>(p)[i];
 }
 __device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, float v) {
     if (dtype == B2ME_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(p)[i] = v;
+    else reinterpret_cast<float*>(p)[i] = dtype == B2ME_TF32 ? round_tf32(v) : v;
 }
 
 // exclusive scan of an int32 array (in place), total written to *total. ws: >= scan_ws_bytes(n)

@@ -816,3 +816,113 @@ extern "C" int b2me_ingest_clouds(const float* xyzrgb, int64_t n, const int32_t*
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
+
+// ------------------------------------------------------------------------------------------ colour normalisation
+// utils/preprocess.py:20-37 (normalize_colors) per FRAME of a batch, on the device, without a host round trip:
+//   max > 2          -> rgb / 255                       (float32 division, like the in-place NumPy op)
+//   min < 0          -> per channel x * scale + min_, scale = 1 / (max - min), min_ = 0 - min * scale
+//                       (sklearn.preprocessing.minmax_scale on a float32 column: two rounded float32 operations)
+//   result in [0, 1] -> rgb - 0.5
+// Pass 1 reduces the per-frame, per-channel extrema (block partials -> ordered-integer atomics), pass 2 applies the
+// three steps with every decision taken from the frame's own extrema (division and the affine map are monotone, so
+// the extrema of the intermediate arrays are the images of the input extrema under the very same float32 operations).
+__device__ __forceinline__ unsigned int f32_to_ordered(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void k_color_stats_init(unsigned int* __restrict__ stats, int F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F * 6) stats[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;  // [min r g b | max r g b], ordered encoding
+}
+
+#define COLOR_SLICES 16
+__global__ void __launch_bounds__(256) k_color_stats(const float* __restrict__ rgb, const int32_t* __restrict__ offs,
+                                                     unsigned int* __restrict__ stats) {
+    const int f = blockIdx.y;
+    const long long o0 = offs[f], o1 = offs[f + 1];
+    const long long len = o1 - o0, per = (len + COLOR_SLICES - 1) / COLOR_SLICES;
+    const long long a = o0 + per * blockIdx.x, b = (a + per < o1) ? a + per : o1;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = a + threadIdx.x; i < b; i += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = rgb[i * 3 + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+    if ((threadIdx.x & 31) == 0 && a < b) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            atomicMin(stats + f * 6 + c, f32_to_ordered(mn[c]));
+            atomicMax(stats + f * 6 + 3 + c, f32_to_ordered(mx[c]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_color_apply(const float* __restrict__ rgb, const float* __restrict__ bidx,
+                                                     int64_t n, int F, const unsigned int* __restrict__ stats,
+                                                     float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f = (int)bidx[i];
+    f = f < 0 ? 0 : (f >= F ? F - 1 : f);
+    float mn[3], mx[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = ordered_to_f32(__ldg(stats + f * 6 + c));
+        mx[c] = ordered_to_f32(__ldg(stats + f * 6 + 3 + c));
+    }
+    float v[3] = {rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2]};
+    if (fmaxf(mx[0], fmaxf(mx[1], mx[2])) > 2.f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            v[c] = __fdiv_rn(v[c], 255.f);
+            mn[c] = __fdiv_rn(mn[c], 255.f);
+            mx[c] = __fdiv_rn(mx[c], 255.f);
+        }
+    }
+    if (fminf(mn[0], fminf(mn[1], mn[2])) < 0.f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float range = __fsub_rn(mx[c], mn[c]);
+            const float scale = __fdiv_rn(1.f, range != 0.f ? range : 1.f);
+            const float min_ = __fsub_rn(0.f, __fmul_rn(mn[c], scale));
+            v[c] = __fadd_rn(__fmul_rn(v[c], scale), min_);   // two rounded operations, never an FMA
+            const float lo = __fadd_rn(__fmul_rn(mn[c], scale), min_), hi = __fadd_rn(__fmul_rn(mx[c], scale), min_);
+            mn[c] = lo;
+            mx[c] = hi;
+        }
+    }
+    if ((double)fminf(mn[0], fminf(mn[1], mn[2])) > -1e-6 && (double)fmaxf(mx[0], fmaxf(mx[1], mx[2])) < 1.0 + 1e-6) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(v[c], 0.5f);
+    }
+    out[i * 3] = v[0];
+    out[i * 3 + 1] = v[1];
+    out[i * 3 + 2] = v[2];
+}
+
+extern "C" int b2me_normalize_colors(const float* rgb, const float* bidx, int64_t n, const int32_t* frame_offsets, int F,
+                                     float* out, void* ws, size_t ws_bytes, b2me_stream_t stream) {
+    if (!rgb || !bidx || !frame_offsets || !out || !ws || n < 0 || F < 1 || F > 65535) return B2ME_EINVAL;
+    if (ws_bytes < (size_t)F * 6 * sizeof(unsigned int)) return B2ME_EWORKSPACE;
+    if (n == 0) return B2ME_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* stats = reinterpret_cast<unsigned int*>(ws);
+    k_color_stats_init<<<(unsigned)((F * 6 + 255) / 256), 256, 0, s>>>(stats, F);
+    k_color_stats<<<dim3(COLOR_SLICES, (unsigned)F), 256, 0, s>>>(rgb, frame_offsets, stats);
+    k_color_apply<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(rgb, bidx, n, F, stats, out);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

@@ -255,3 +255,200 @@ extern "C" int b2me_translation_magic(const float* points_xyz, const int32_t* se
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
+
+// ------------------------------------------------------------------------------------------ sanity check
+// InferenceEngine.check_sanity (app/inference_engine.py:246-279) with get_6_key_points (utils/data.py:255-335,
+// switch_w = False, euclidean_threshold = 0.04) and compute_kp_error (utils/metrics.py:130-136), batched: one CTA per
+// EE crop, float64 like the reference's NumPy. Two passes over the crop: (1) EE-frame coordinates, the four corner
+// arg-mins over the "front" points, the largest z of each gripper side; (2) the gripper points nearest to the lifted
+// probes. Arg-mins keep the lowest index among equal distances (np.argmin).
+struct SanityArg {
+    double v;
+    int i;
+};
+__device__ __forceinline__ SanityArg sanity_min(SanityArg a, SanityArg b) {
+    return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ SanityArg sanity_block_argmin(SanityArg x, SanityArg* sh) {
+    for (int o = 16; o > 0; o >>= 1) {
+        SanityArg y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        x = sanity_min(x, y);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    SanityArg r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = sanity_min(r, sh[w]);
+    return r;
+}
+__device__ __forceinline__ double sanity_block_max(double x, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double r = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, sh[w]);
+    return r;
+}
+__device__ __forceinline__ int sanity_block_sum(int x, int* sh) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int r = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += sh[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_sanity_check(const float* __restrict__ pts, const int32_t* __restrict__ seg_offsets, const double* __restrict__ poses,
+               const float* __restrict__ kp_prob, const float* __restrict__ kp_xyz, int K, float kp_threshold,
+               int min_points, double kp_margin, uint8_t* __restrict__ out_confident) {
+    __shared__ SanityArg sh_arg[8];
+    __shared__ double sh_d[8];
+    __shared__ int sh_i[8];
+    // utils/data.py:264-271 key-point template and :280-285 corner probes (EE frame)
+    const double tmpl[6][3] = {{0.02, 0.09, 0.0}, {0.01, -0.1, 0.0}, {0.014, 0.095, 0.07}, {0.014, -0.095, 0.07},
+                               {0.0, 0.048, 0.12}, {0.0, -0.048, 0.12}};
+    const double probe[4][3] = {{0.24, 0.32, -0.2}, {0.24, -0.32, -0.2}, {0.24, 0.32, 0.2}, {0.24, -0.32, 0.2}};
+    const int seg = blockIdx.x;
+    const int r0 = seg_offsets[seg], r1 = seg_offsets[seg + 1];
+    const int n = r1 - r0;
+    const double* pose = poses + (int64_t)seg * 7;
+    const double q0 = pose[3], q1 = pose[4], q2 = pose[5], q3 = pose[6];
+    const double R[3][3] = {{2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2)},
+                            {2 * (q1 * q2 + q0 * q3), 2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1)},
+                            {2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 2 * (q0 * q0 + q3 * q3) - 1}};
+    double origin[3];
+    for (int c = 0; c < 3; ++c) origin[c] = pose[0] * R[0][c] + pose[1] * R[1][c] + pose[2] * R[2][c];
+    auto local_of = [&](int r, double* l) {
+        const double x = pts[(int64_t)r * 3], y = pts[(int64_t)r * 3 + 1], z = pts[(int64_t)r * 3 + 2];
+        for (int c = 0; c < 3; ++c) l[c] = (x * R[0][c] + y * R[1][c] + z * R[2][c]) - origin[c];
+    };
+    int nkp = 0;  // predicted key points above the confidence threshold (ResultDTO.key_points)
+    if (kp_prob)
+        for (int k = 0; k < K; ++k) nkp += kp_prob[(int64_t)seg * K + k] > kp_threshold ? 1 : 0;
+
+    // ---- pass 1
+    SanityArg corner[4];
+    for (int c = 0; c < 4; ++c) { corner[c].v = INFINITY; corner[c].i = 0x7FFFFFFF; }
+    int nfront = 0, cnt_a = 0, cnt_b = 0;
+    double maxz_a = -INFINITY, maxz_b = -INFINITY;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        double l[3];
+        local_of(r, l);
+        if (l[0] > -0.005 && l[2] < 0.09) {
+            ++nfront;
+            for (int c = 0; c < 4; ++c) {
+                const double dx = probe[c][0] - l[0], dy = probe[c][1] - l[1], dz = probe[c][2] - l[2];
+                SanityArg cand;
+                cand.v = sqrt(dx * dx + dy * dy + dz * dz);
+                cand.i = r - r0;
+                corner[c] = sanity_min(corner[c], cand);
+            }
+        }
+        if (l[2] > 0.08) {
+            if (l[1] > 0) { ++cnt_a; maxz_a = fmax(maxz_a, l[2]); }
+            if (l[1] < 0) { ++cnt_b; maxz_b = fmax(maxz_b, l[2]); }
+        }
+    }
+    for (int c = 0; c < 4; ++c) corner[c] = sanity_block_argmin(corner[c], sh_arg);
+    nfront = sanity_block_sum(nfront, sh_i);
+    cnt_a = sanity_block_sum(cnt_a, sh_i);
+    cnt_b = sanity_block_sum(cnt_b, sh_i);
+    maxz_a = sanity_block_max(maxz_a, sh_d);
+    maxz_b = sanity_block_max(maxz_b, sh_d);
+
+    // ---- pass 2: gripper points nearest to the probes lifted to the largest z of their side (get_closest_point)
+    SanityArg grip[2];
+    grip[0].v = grip[1].v = INFINITY;
+    grip[0].i = grip[1].i = 0x7FFFFFFF;
+    if (nkp > 3 && (cnt_a > 0 || cnt_b > 0)) {
+        for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            double l[3];
+            local_of(r, l);
+            if (l[2] > 0.08) {
+                if (l[1] > 0) {
+                    const double dy = l[1] - 0.01, dz = l[2] - maxz_a;
+                    SanityArg cand;
+                    cand.v = sqrt(l[0] * l[0] + dy * dy + dz * dz);
+                    cand.i = r - r0;
+                    grip[0] = sanity_min(grip[0], cand);
+                }
+                if (l[1] < 0) {
+                    const double dy = l[1] + 0.01, dz = l[2] - maxz_b;
+                    SanityArg cand;
+                    cand.v = sqrt(l[0] * l[0] + dy * dy + dz * dz);
+                    cand.i = r - r0;
+                    grip[1] = sanity_min(grip[1], cand);
+                }
+            }
+        }
+    }
+    grip[0] = sanity_block_argmin(grip[0], sh_arg);
+    grip[1] = sanity_block_argmin(grip[1], sh_arg);
+    if (threadIdx.x != 0) return;
+
+    // ---- verdict (app/inference_engine.py:252-279)
+    uint8_t ok = 1;
+    if (n < min_points) {
+        ok = 0;                                            // "fail min # points"
+    } else if (nfront < 1) {
+        // get_6_key_points returns empty arrays: the corner test is vacuous, compute_kp_error returns 100
+        if (nkp > 3 && 100.0 > kp_margin) ok = 0;
+    } else {
+        double kps[6][3];
+        for (int k = 0; k < 6; ++k)
+            for (int c = 0; c < 3; ++c) kps[k][c] = tmpl[k][c];
+        for (int c = 0; c < 4 && ok; ++c) {
+            double l[3];
+            local_of(r0 + corner[c].i, l);
+            const double dx = tmpl[c][0] - l[0], dy = tmpl[c][1] - l[1], dz = tmpl[c][2] - l[2];
+            if (sqrt(dx * dx + dy * dy + dz * dz) < 0.04) {
+                for (int a = 0; a < 3; ++a) kps[c][a] = l[a];
+            } else {
+                ok = 0;                                    // "fail dim check": a corner is not where the pose puts it
+            }
+        }
+        if (ok && nkp > 3) {
+            bool found[2] = {cnt_a > 0, cnt_b > 0};
+            for (int sd = 0; sd < 2; ++sd)
+                if (found[sd]) local_of(r0 + grip[sd].i, kps[4 + sd]);
+            if (!found[0] && found[1]) { kps[4][0] = kps[5][0]; kps[4][1] = -kps[5][1]; kps[4][2] = kps[5][2]; }
+            else if (found[0] && !found[1]) { kps[5][0] = kps[4][0]; kps[5][1] = -kps[4][1]; kps[5][2] = kps[4][2]; }
+            const double zz = fmax(kps[4][2], kps[5][2]);
+            kps[4][2] = kps[5][2] = zz;
+            double err = 0.0;
+            int cnt = 0;
+            for (int k = 0; k < K; ++k) {
+                if (!(kp_prob[(int64_t)seg * K + k] > kp_threshold)) continue;
+                if (k >= 6) { err = INFINITY; ++cnt; continue; }   // no such template key point
+                double cam[3];
+                for (int r = 0; r < 3; ++r)
+                    cam[r] = (kps[k][0] + origin[0]) * R[r][0] + (kps[k][1] + origin[1]) * R[r][1] +
+                             (kps[k][2] + origin[2]) * R[r][2];
+                const float* pk = kp_xyz + ((int64_t)seg * K + k) * 3;   // float32 coordinates, like the reference's array
+                const double dx = cam[0] - (double)pk[0], dy = cam[1] - (double)pk[1], dz = cam[2] - (double)pk[2];
+                err += sqrt(dx * dx + dy * dy + dz * dz);
+                ++cnt;
+            }
+            if (cnt >= 2 && err / cnt > kp_margin) ok = 0;  // "fail kp error margin"
+        }
+    }
+    out_confident[seg] = ok;
+}
+
+extern "C" int b2me_sanity_check(const float* points_xyz, const int32_t* seg_offsets, int S, const double* ee_pose,
+                                 const float* kp_prob, const float* kp_xyz, int K, float kp_threshold, int min_points,
+                                 double kp_margin, uint8_t* out_confident, b2me_stream_t stream) {
+    if (!points_xyz || !seg_offsets || !ee_pose || !out_confident || S < 0 || K < 0) return B2ME_EINVAL;
+    if (K > 0 && (!kp_prob || !kp_xyz)) return B2ME_EINVAL;
+    if (S == 0) return B2ME_OK;
+    k_sanity_check<<<(unsigned)S, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        points_xyz, seg_offsets, ee_pose, K > 0 ? kp_prob : nullptr, kp_xyz, K, kp_threshold, min_points, kp_margin,
+        out_confident);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

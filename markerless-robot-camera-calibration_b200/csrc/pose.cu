@@ -129,12 +129,12 @@ extern "C" int b2me_kabsch_batched(const double* ref, const double* tgt, const i
 
 // ------------------------------------------------------------------------------------------ K10
 // Batched point-to-point ICP. Per frame: the target (EE) points are binned once into a dense uniform grid
-// (<= 20^3 cells, cell >= 2 cm, counting sort). Every ICP evaluation is ONE launch over (source chunks x
-// frames): a thread transforms one CAD point with the frame's current 4x4 (fp64), finds its EXACT nearest
-// target within max_corr by an expanding-ring search over the grid (cell offsets staged in shared memory),
-// and the CTA reduces the 17 Kabsch sums in a fixed order into a per-(frame, chunk) slot. The last CTA of a
-// frame to finish (ticket counter) adds the chunk slots in chunk order (deterministic), applies the
-// convergence test and the Kabsch update of Open3D's RegistrationICP loop and arms the next evaluation.
+// (<= 20^3 cells, cell >= 2 cm, counting sort). The whole ICP loop is ONE launch (k_icp_persistent): a thread-block
+// cluster per frame keeps the frame's targets in shared memory across all evaluations; a thread transforms a CAD
+// point with the frame's current 4x4 (fp64), finds its EXACT nearest target within max_corr by a sphere-bounded
+// search over the grid, the CTAs reduce the 17 Kabsch sums in a fixed order into per-CTA slots, and rank 0 of the
+// cluster adds the slots in rank order (deterministic), applies the convergence test and the Kabsch update of
+// Open3D's RegistrationICP loop; a frame leaves the loop when it has converged.
 #define ICP_GRID 20
 #define ICP_CELLS (ICP_GRID * ICP_GRID * ICP_GRID)
 #define ICP_MIN_CELL 0.02
@@ -422,13 +422,38 @@ __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const 
 }
 
 #define ICP_EVAL_THREADS 512
+#define ICP_EVAL_SMEM (200 * 1024)  // dynamic smem of k_icp_persistent: cell offsets + as many target points as fit
+#define ICP_MAX_CLUSTER 8
+
+__device__ __forceinline__ unsigned icp_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned icp_cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// cluster-wide barrier with release / acquire ordering of global memory between the CTAs of the cluster
+__device__ __forceinline__ void icp_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ONE launch for the whole ICP loop. A thread-block CLUSTER (1, 2, 4 or 8 CTAs: as many as the GPU has room for) owns
+// one frame: every CTA stages the frame's cell-sorted targets and cell offsets in its shared memory ONCE and takes
+// the source points rank * 512 + tid + q * (cluster size * 512) of every evaluation. Per evaluation: queries ->
+// fixed-order block reduction of the 17 Kabsch sums -> this CTA's slot in global memory -> cluster barrier -> rank 0
+// adds the slots in rank order, applies Open3D's stopping rule and the Kabsch update (icp_frame_update) -> cluster
+// barrier -> every CTA re-reads T / done. Frames leave the loop as soon as they have converged (no launches for
+// finished frames, no reload of the targets per evaluation, no atomics: results do not depend on scheduling).
 __global__ void __launch_bounds__(ICP_EVAL_THREADS)
-k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
-           const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
-           const float4* __restrict__ sorted, int32_t* __restrict__ match_all, IcpState* __restrict__ state,
-           double* __restrict__ partial_all,
-           int ev, int tcap, double max_corr, int max_iter, double rel_fitness, double rel_rmse,
-           double* __restrict__ out_T, double* __restrict__ out_stats) {
+k_icp_persistent(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
+                 const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
+                 const float4* __restrict__ sorted, int32_t* __restrict__ match_all, IcpState* __restrict__ state,
+                 double* __restrict__ partial_all, int tcap, double max_corr, int max_iter, double rel_fitness,
+                 double rel_rmse, double* __restrict__ out_T, double* __restrict__ out_stats) {
     extern __shared__ __align__(16) unsigned char icp_smem[];
     float4* tg_s = reinterpret_cast<float4*>(icp_smem);
     int* cs = reinterpret_cast<int*>(icp_smem + (size_t)tcap * sizeof(float4));
@@ -436,14 +461,11 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
     __shared__ double red[ICP_EVAL_THREADS / 32][ICP_NSUM];
     __shared__ double tot[ICP_NSUM];
     __shared__ IcpFrameGrid g;
-    __shared__ int last_s;
-    const int f = blockIdx.y;
-    const int nchunk = gridDim.x;
+    const int csize = (int)icp_cluster_size(), rank = (int)icp_cluster_rank();
+    const int f = blockIdx.x / csize;
     IcpState* st = state + f;
-    if (st->done) return;  // uniform for the CTA; written only by the frame's last CTA of an earlier launch
     const int t0 = tgt_offsets[f];
     const int nT = tgt_offsets[f + 1] - t0;
-    if (threadIdx.x < 12) T_s[threadIdx.x] = st->T[threadIdx.x];
     if (threadIdx.x == 0) g = grids[f];
     __syncthreads();
     const int ncell = g.dims[0] * g.dims[1] * g.dims[2];
@@ -454,69 +476,70 @@ k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt
     const bool in_smem = nT <= tcap;
     if (in_smem)
         for (int i = threadIdx.x; i < nT; i += blockDim.x) tg_s[i] = __ldg(sorted + t0 + i);
-    __syncthreads();
     const double R2 = max_corr * max_corr;
-    double acc[ICP_NSUM];
+    int32_t* match = match_all + (int64_t)f * S;
+    double* partial = partial_all + (int64_t)f * ICP_MAX_CHUNKS * ICP_NSUM;
+    const int stride = csize * ICP_EVAL_THREADS;
+    for (int ev = 0; ev <= max_iter; ++ev) {
+        // the state of this frame as rank 0 left it (ordered by the cluster barrier at the end of the previous round)
+        if (threadIdx.x < 12) T_s[threadIdx.x] = __ldcg(st->T + threadIdx.x);
+        __syncthreads();
+        double acc[ICP_NSUM];
 #pragma unroll
-    for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
-    if (nT > 0) {
-        int32_t* match = match_all + (int64_t)f * S;
-        for (int i = blockIdx.x * ICP_EVAL_THREADS + threadIdx.x; i < S; i += nchunk * ICP_EVAL_THREADS) {
-            const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
-            const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
-            const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
-            const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
-            double best, bx = 0, by = 0, bz = 0;
-            int best_j, best_s;
-            const int seed = ev > 0 ? match[i] : -1;
-            if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
-            else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
-            match[i] = best_s;
-            if (best_j != 0x7FFFFFFF) {
-                acc[0] += 1.0; acc[1] += best;
-                acc[2] += px; acc[3] += py; acc[4] += pz;
-                acc[5] += bx; acc[6] += by; acc[7] += bz;
-                acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
-                acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
-                acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
+        for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
+        if (nT > 0) {
+            for (int i = rank * ICP_EVAL_THREADS + threadIdx.x; i < S; i += stride) {
+                const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
+                const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
+                const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
+                const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
+                double best, bx = 0, by = 0, bz = 0;
+                int best_j, best_s;
+                const int seed = ev > 0 ? match[i] : -1;  // written by this very thread in the previous evaluation
+                if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+                else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+                match[i] = best_s;
+                if (best_j != 0x7FFFFFFF) {
+                    acc[0] += 1.0; acc[1] += best;
+                    acc[2] += px; acc[3] += py; acc[4] += pz;
+                    acc[5] += bx; acc[6] += by; acc[7] += bz;
+                    acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
+                    acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
+                    acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
+                }
             }
         }
-    }
-    // fixed-order block reduction -> this chunk's slot
+        // fixed-order block reduction -> this CTA's slot
 #pragma unroll
-    for (int q = 0; q < ICP_NSUM; ++q) {
-        double v = acc[q];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+        for (int q = 0; q < ICP_NSUM; ++q) {
+            double v = acc[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < ICP_NSUM) {
+            double v = 0.0;
+            for (int wv = 0; wv < ICP_EVAL_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+            if (csize == 1) tot[threadIdx.x] = v;
+            else __stcg(partial + rank * ICP_NSUM + threadIdx.x, v);
+        }
+        if (csize > 1) {
+            icp_cluster_sync();  // every CTA's slot is written and visible
+            if (rank == 0 && threadIdx.x < ICP_NSUM) {
+                double v = 0.0;
+                for (int c = 0; c < csize; ++c) v += __ldcg(partial + c * ICP_NSUM + threadIdx.x);
+                tot[threadIdx.x] = v;
+            }
+        }
+        __syncthreads();
+        if (rank == 0 && threadIdx.x == 0) {
+            icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
+            __threadfence();
+        }
+        icp_cluster_sync();  // the new T / done of the frame are visible to every CTA of its cluster
+        if (__ldcg(&st->done)) break;  // same value in every thread of the cluster
     }
-    __syncthreads();
-    double* partial = partial_all + (int64_t)f * ICP_MAX_CHUNKS * ICP_NSUM;
-    if (threadIdx.x < ICP_NSUM) {
-        double v = 0.0;
-        for (int wv = 0; wv < ICP_EVAL_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
-        partial[blockIdx.x * ICP_NSUM + threadIdx.x] = v;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(&st->counter, 1u);
-        last_s = (ticket == (unsigned int)(nchunk - 1)) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!last_s) return;
-    // ---- last CTA of the frame: chunk slots in chunk order, convergence test, Kabsch update
-    __threadfence();
-    if (threadIdx.x < ICP_NSUM) {
-        double v = 0.0;
-        for (int c = 0; c < nchunk; ++c) v += __ldcg(partial + c * ICP_NSUM + threadIdx.x);
-        tot[threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-        icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
 }
-
-#define ICP_EVAL_SMEM (200 * 1024)  // dynamic smem of k_icp_eval: cell offsets + as many target points as fit
 
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
@@ -526,28 +549,41 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     if (!target_xyz && T_total > 0) return B2ME_EINVAL;  // an empty target cloud may come with a null pointer
     if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
     if (F == 0) return B2ME_OK;
-    if (F > 65535) return B2ME_EUNSUPPORTED;  // gridDim.y
+    if (F > (1 << 20)) return B2ME_EUNSUPPORTED;
     IcpWs w = carve_icp_ws(ws, T_total, F, S);
     if (ws_bytes < w.total) return B2ME_EWORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     k_icp_build_grid<<<(unsigned)F, ICP_THREADS, 0, s>>>(target_xyz, tgt_offsets, init_T, w.grids, w.state,
                                                          w.cell_start, w.cell_cursor, w.sorted);
-    int nchunk = (S + ICP_EVAL_THREADS - 1) / ICP_EVAL_THREADS;
-    if (nchunk > ICP_MAX_CHUNKS) nchunk = ICP_MAX_CHUNKS;
-    const dim3 grid((unsigned)nchunk, (unsigned)F);
     const size_t smem = ICP_EVAL_SMEM;
     const int tcap = (int)((smem - (size_t)(ICP_CELLS + 1) * sizeof(int)) / sizeof(float4));
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_icp_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return B2ME_ELAUNCH;
-        attr_set = true;
-    }
+    // per-device attribute: set on every call (cheap) so that a process driving several GPUs works
+    if (cudaFuncSetAttribute(k_icp_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return B2ME_ELAUNCH;
+    // cluster size: as many CTAs per frame as the SMs allow (1 CTA per SM at 200 KB of shared memory), at most one
+    // CTA per 512 source points
+    int dev = 0, sms = B2ME_NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int csize = 1;
+    while (csize < ICP_MAX_CLUSTER && 2 * csize * F <= sms && 2 * csize * ICP_EVAL_THREADS <= S + ICP_EVAL_THREADS - 1)
+        csize *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(F * csize), 1, 1);
+    cfg.blockDim = dim3(ICP_EVAL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
-    for (int ev = 0; ev <= max_iter; ++ev)
-        k_icp_eval<<<grid, ICP_EVAL_THREADS, smem, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted,
-                                                        w.match, w.state, w.partial, ev, tcap, max_corr, max_iter,
-                                                        rel_fitness, rel_rmse, out_T, out_stats);
+    if (cudaLaunchKernelEx(&cfg, k_icp_persistent, source_xyz, S, tgt_offsets, (const IcpFrameGrid*)w.grids,
+                           (const int32_t*)w.cell_start, (const float4*)w.sorted, w.match, w.state, w.partial, tcap,
+                           max_corr, max_iter, rel_fitness, rel_rmse, out_T, out_stats) != cudaSuccess)
+        return B2ME_ELAUNCH;
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -146,6 +146,10 @@ k_spconv_stem(const float* __restrict__ in, int Cin, const float* __restrict__ W
                 op[q] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             }
         } else {
+            if (out_dtype == B2ME_TF32) {
+#pragma unroll
+                for (int n = 0; n < STEM_COUT; ++n) acc[n] = round_tf32(acc[n]);
+            }
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * STEM_COUT);
 #pragma unroll
             for (int q = 0; q < 8; ++q) op[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
@@ -161,7 +165,7 @@ extern "C" int b2me_spconv_fwd_simt(const void* in1, int Cin1, const void* in2, 
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
     if (V_out == 0) return B2ME_OK;
-    if (Cin2 == 0 && Cin1 <= 4 && Cout == STEM_COUT && K <= 27 && in_dtype == B2ME_F32 && !residual) {
+    if (Cin2 == 0 && Cin1 <= 4 && Cout == STEM_COUT && K <= 27 && (in_dtype == B2ME_F32 || in_dtype == B2ME_TF32) && !residual) {
         int64_t blocks = ceil_div64(V_out, 256);
         if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
         const size_t smem = (size_t)K * Cin1 * STEM_COUT * sizeof(float);

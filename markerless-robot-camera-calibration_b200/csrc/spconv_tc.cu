@@ -1,23 +1,33 @@
 // spconv_tc.cu — K4b: sparse convolution as an output-stationary implicit GEMM on tcgen05 (sm_100a).
 //
 // PERSISTENT, warp-specialised kernel on CTA PAIRS (cta_group::2): a cluster of two CTAs (one TPC) walks the work
-// list (256-row tile pair x n-tile) round-robin; each CTA gathers the A rows of its own 128-row tile and loads HALF
-// of every weight tile, the leader CTA issues M = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM
-// holds the accumulator of its own 128 rows. Halving the per-SM weight traffic is what lets the stage ring be deep
-// enough (4 x 40 KB at n_tile = 384) to cover the DRAM latency of the gathered rows.
+// list (256-row tile pair x n-tile; the n-tiles of one tile pair run back to back on the same cluster) round-robin;
+// each CTA gathers the A rows of its own 128-row tile and loads HALF of every weight tile, the leader CTA issues
+// M = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM holds the accumulator of its own 128 rows.
+// Halving the per-SM weight traffic is what lets the stage ring be deep enough (4 x 40 KB at n_tile = 384) to cover
+// the DRAM latency of the gathered rows.
 //
+//   operand types ES = 2: bf16 x bf16 (kind::f16), 64 channels per 128-byte chunk, K = 16 per MMA
+//                 ES = 4: tf32 x tf32 (kind::tf32) on fp32 rows, 32 channels per 128-byte chunk, K = 8 per MMA; the
+//                         rows and the packed weights hold tf32-representable values (rounded to nearest by the
+//                         producing epilogue / the weight pack), so the tensor core's truncation is exact
 //   work item     2 x 128 output voxels (rows perm[256 t ..]) x n_tile output channels (n_tile <= 384 TMEM columns)
-//   reduction     items = (kernel offset k with at least one neighbour in the tile) x (64-channel chunk)
-//   A operand     128 gathered input rows x 64 bf16 (= one 128-byte swizzle row per voxel), cp.async 16-byte
-//                 pieces straight into the SWIZZLE_128B K-major smem image, zero-fill for missing neighbours
+//   reduction     items = (kernel offset k with at least one neighbour in the tile pair) x (128-byte channel chunk)
+//   A operand     128 gathered input rows x 128 bytes (= one swizzle row per voxel), cp.async 16-byte pieces
+//                 straight into the SWIZZLE_128B K-major smem image, zero-fill for missing neighbours
 //   B operand     W[k][chunk] pre-packed on the host side of the ABI into the exact smem image of each CTA's half,
 //                 so one cp.async.bulk (UBLKCP) per item brings n_tile/2 x 128 bytes and completes on the stage
 //                 mbarrier
-//   MMA           one elected thread of the leader CTA issues tcgen05.mma.cta_group::2.kind::f16 (M=256, N<=256,
-//                 K=16), fp32 accumulators stay in TMEM for the whole tile; tcgen05.commit multicasts the stage
-//                 release / accumulator-ready arrivals to both CTAs
+//   MMA           one elected thread of the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N<=256), fp32
+//                 accumulators stay in TMEM for the whole tile; tcgen05.commit multicasts the stage release /
+//                 accumulator-ready arrivals to both CTAs
 //   epilogue      tcgen05.ld -> folded BatchNorm scale/shift, residual add, ReLU/LeakyReLU -> bf16 rows, staged
 //                 through shared memory so that residual loads and output stores are 64-byte coalesced segments
+//   fused head    (b2me_head_fused_tc) K = 1, Cin -> Cout hidden units (n-tiles of <= 256 columns) + activation, then
+//                 the small second linear Cout -> C (C <= 16) INSIDE the epilogue: every epilogue lane keeps the C
+//                 partial logits of its row in registers across the n-tiles, the two column halves are combined
+//                 through shared memory, and only [V, C] logits + the per-row arg-max reach HBM (the hidden
+//                 activation never does). model/robotnet_segmentation.py:43-49.
 //
 //   warps  0-3    gather producers (stage ring runs on across tiles, so the next tile's rows are in flight while
 //                 the tensor pipe finishes the current one); prefetch.global.L2 of the next offset's rows
@@ -25,19 +35,26 @@
 //                 loop is warp-uniform: shfl-broadcast warp index / tile masks / TMEM base, one elect.sync branch
 //                 per item, descriptors as 32-bit low words -> UTCHMMA operands live in uniform registers
 //          5      weight (B) bulk-copy issuer
-//          6-7    kernel-map prefetch: the NEXT tile's 128 x K neighbour rows go global -> registers while the
+//          6-7    kernel-map prefetch: the NEXT item's 128 x K neighbour rows go global -> registers while the
 //                 current tile runs, then registers -> smem the moment the producers release the buffer
 //          8-15   epilogue (warp w owns TMEM lanes 32 (w % 4) .. and the column half (w - 8) / 4); overlaps the
-//                 next tile's gathers, and its MMAs when two accumulators fit TMEM (n_tile <= 256)
+//                 next tile's gathers, and its MMAs when TMEM has room (see accumulators)
+//
+//   accumulators  n_tile <= 256: two buffers of n_tile columns alternate, the epilogue of tile i overlaps the MMAs
+//                 of tile i + 1.  n_tile = 384 (256 + 128 columns, the K = 27 / 8 layers): the 256-column part lives
+//                 in TMEM columns [0, 256) and is released as soon as its four 32-column chunks per warp are read,
+//                 the 128-column part alternates between columns [256, 384) and [384, 512): the next tile's MMAs
+//                 start after two thirds of the drain instead of after all of it (B2ME_TC_FLAG_NO_ROT128 = single
+//                 384-column accumulator, the round-1 layout).
 //
 //   barriers      full[s]  (128 cp.async-completion arrivals + 1 expect_tx + the peer's relay on the leader)
 //                 empty[s] (tcgen05.commit, multicast to both CTAs)
 //                 nbr_full (2 prefetch warps)                        nbr_empty    (4 producer warps)
-//                 tmem_full[2] (commit) / tmem_empty[2] (8 epilogue warps of each CTA, on the leader)
+//                 tmem_full[2] (commit) / tmem_empty[3] (8 epilogue warps of each CTA, on the leader)
 //
-//   B2ME_TC_TMA=1 operands through the TMA unit instead: tile::gather4 copies of the gathered rows (absent neighbour =
-//                 row -1 = out of bounds = zeros) and 2-D boxes of the packed weights, cta_group::2 with the LEADER's
-//                 stage barrier as completion target - no relay, no proxy fence; same speed, kept opt-in
+//   B2ME_TC_FLAG_TMA  operands through the TMA unit instead: tile::gather4 copies of the gathered rows (absent
+//                 neighbour = row -1 = out of bounds = zeros) and 2-D boxes of the packed weights, cta_group::2 with
+//                 the LEADER's stage barrier as completion target - no relay, no proxy fence; same speed
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"
@@ -45,22 +62,11 @@
 #include <stdlib.h>
 
 #define TC_BM 128
-#define TC_BK 64
 #define TC_A_BYTES (TC_BM * 128)
 #define TC_THREADS 512
 #define TC_EPI_WARPS 8
 #ifndef TC_L2_PREFETCH
 #define TC_L2_PREFETCH 1  // producers prefetch the next offset's rows into L2
-#endif
-#ifndef TC_GI
-#define TC_GI 1  // (offset, chunk) items per stage = per barrier round. 2 (fewer, larger rounds; 2 stages at n_tile 384) measured slower: 776 vs 837 TFLOP/s
-#endif
-static_assert(TC_GI == 1 || TC_GI == 2, "the B loader announces 1 or TC_GI items per group");
-#ifndef TC_EPI_STAGED
-#define TC_EPI_STAGED 1  // residual / output rows staged through smem for 64-byte coalesced segments (0: row per lane)
-#endif
-#ifndef TC_A_COLLECTOR
-#define TC_A_COLLECTOR 0
 #endif
 #ifndef TC_NSPLIT0
 #define TC_NSPLIT0 256  // N of the first MMA of a K step when the tile is wider than 256 columns
@@ -69,29 +75,37 @@ static_assert(TC_GI == 1 || TC_GI == 2, "the B loader announces 1 or TC_GI items
 #define TC_MAX_SMEM 232448
 #define TC_MIN_SMEM (120 * 1024)  // more than half an SM: one CTA per SM, so a 512-column TMEM alloc never blocks
 #define TC_STAGE_OUT_BYTES 2048   // per epilogue warp: 32 rows x 64 bytes
+#define TC_HEAD_MAX 16            // classes of the fused second linear
 
 struct TcParams {
-    const __nv_bfloat16* in1;
-    const __nv_bfloat16* in2;
+    const uint8_t* in1;  // rows of Cin1 * ES bytes
+    const uint8_t* in2;
     const uint8_t* wpacked;
     const int32_t* nbr;
     const int32_t* perm;
     const uint32_t* tile_masks;
     const float* scale;
     const float* shift;
-    const __nv_bfloat16* residual;
+    const void* residual;  // bf16 rows (ES = 2) / f32 rows (ES = 4)
     void* out;
+    // fused head (null head_w = plain convolution)
+    const float* head_w;   // [Cout, head_cp] f32, zero padded columns
+    const float* head_b;   // [head_c] or null
+    float* head_logits;    // [V_out, head_c]
+    uint8_t* head_argmax;  // [V_out] or null
     long long V_out;
     int Cin1, Cin2, nchunk1, nchunk2;
     int Cout, n_tile, n_ntiles, stages;
     int act, out_dtype, tmem_cols;
     int acc_bufs;  // 2 when two accumulators fit TMEM (2 n_tile <= 512): the epilogue overlaps the next tile's MMAs
+    int rot128;    // n_tile = 384: 256-column part released early, 128-column part alternates between two regions
+    int head_c, head_cp;
     float slope;
     unsigned int b_bytes;
-    int total_work;  // 256-row tile pairs x n-tiles
-    int debug;       // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
-    int tma;         // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
-    // tensor maps (TMA mode): the two sources as [V_in, Cin] bf16 with a 64-channel x 1-row box (SWIZZLE_128B; rows are
+    int n_pairs;  // 256-row tile pairs
+    int debug;    // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
+    int tma;      // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
+    // tensor maps (TMA mode): the two sources as [V_in, Cin] with a (128-byte chunk) x 1-row box (SWIZZLE_128B; rows are
     // picked by tile::gather4, absent neighbours (-1) and channels past Cin are out of bounds = zero-filled) and the
     // packed weights as 128-byte rows (box = one CTA's half of an item, no swizzle: the image is pre-swizzled)
     alignas(64) CUtensorMap tm_in1;
@@ -147,29 +161,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-#ifndef TC_SPIN_WAIT
-#define TC_SPIN_WAIT 0  // 1: poll with mbarrier.test_wait (never suspends) instead of try_wait
-#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-#if TC_SPIN_WAIT
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > (1u << 28)) __trap();
-    }
-#else
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
-#endif
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -180,11 +176,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -218,22 +209,6 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// SWIZZLE_128B, K-major, 8-row groups 1024 B apart, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -243,8 +218,6 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -275,54 +248,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
         "r"(rank)
         : "memory");
 }
-// wait whose acquire covers arrivals made by the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > (1u << 26)) __trap();
-    }
-}
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
         "h"((uint16_t)3)
         : "memory");
-}
-// COLL: 0 = default (A discarded after use), 1 = collector::a::fill (keep the A slice in the collector buffer),
-// 2 = collector::a::lastuse (reuse the kept A slice: no second shared-memory read of A)
-template <int COLL>
-__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-    if (COLL == 1) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else if (COLL == 2) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
 }
 // one lane of the (converged) warp: true in exactly one lane
 __device__ __forceinline__ bool tc_elect_one() {
@@ -330,67 +260,26 @@ __device__ __forceinline__ bool tc_elect_one() {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred)::"memory");
     return pred != 0;
 }
-// tcgen05.mma with descriptors given as low words (see below), executed by the calling thread
+// tcgen05.mma of a CTA pair, executed by the calling thread. Descriptors are passed as their low words (start address
+// >> 4 | LBO field); the high word of the SWIZZLE_128B K-major descriptor (SBO 1024 B, version 1, swizzle mode 2) is the
+// constant 0x40004040. ES = 2: kind::f16 (bf16 operands), ES = 4: kind::tf32.
+template <int ES>
 __device__ __forceinline__ void tc_mma_lo(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
-        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
-        : "memory");
-}
-// Warp-uniform issue helpers: ALL lanes execute the statement with identical operands, elect.sync picks the issuing
-// lane inside the block. Descriptors are passed as their low words (start address >> 4 | LBO field); the high word of
-// the SWIZZLE_128B K-major descriptor (SBO 1024 B, version 1, swizzle mode 2) is the constant 0x40004040.
-// FENCE: the elected lane first orders the generic-proxy (cp.async) writes of the stage before its async-proxy reads.
-template <bool FENCE>
-__device__ __forceinline__ void tc_kstep2(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b0_lo, uint32_t b1_lo,
-                                          uint32_t idesc0, uint32_t idesc1, uint32_t accumulate) {
-    if (FENCE) {
+    if (ES == 2) {
         asm volatile(
-            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0, db1;\n\t"
-            "elect.sync _|q, 0xffffffff;\n\t"
-            "setp.ne.b32 p, %7, 0;\n\t"
-            "mov.b64 da, {%2, %8};\n\tmov.b64 db0, {%3, %8};\n\tmov.b64 db1, {%4, %8};\n\t"
-            "@q fence.proxy.async.shared::cta;\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %5, p;\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da, db1, %6, p;\n\t}" ::"r"(d0),
-            "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(idesc0), "r"(idesc1), "r"(accumulate), "r"(0x40004040u)
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+            "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
             : "memory");
     } else {
         asm volatile(
-            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0, db1;\n\t"
-            "elect.sync _|q, 0xffffffff;\n\t"
-            "setp.ne.b32 p, %7, 0;\n\t"
-            "mov.b64 da, {%2, %8};\n\tmov.b64 db0, {%3, %8};\n\tmov.b64 db1, {%4, %8};\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %5, p;\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%1], da, db1, %6, p;\n\t}" ::"r"(d0),
-            "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(idesc0), "r"(idesc1), "r"(accumulate), "r"(0x40004040u)
-            : "memory");
-    }
-}
-template <bool FENCE>
-__device__ __forceinline__ void tc_kstep1(uint32_t d0, uint32_t a_lo, uint32_t b0_lo, uint32_t idesc0,
-                                          uint32_t accumulate) {
-    if (FENCE) {
-        asm volatile(
-            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0;\n\t"
-            "elect.sync _|q, 0xffffffff;\n\t"
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "mov.b64 da, {%1, %5};\n\tmov.b64 db0, {%2, %5};\n\t"
-            "@q fence.proxy.async.shared::cta;\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %3, p;\n\t}" ::"r"(d0),
-            "r"(a_lo), "r"(b0_lo), "r"(idesc0), "r"(accumulate), "r"(0x40004040u)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db0;\n\t"
-            "elect.sync _|q, 0xffffffff;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "mov.b64 da, {%1, %5};\n\tmov.b64 db0, {%2, %5};\n\t"
-            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db0, %3, p;\n\t}" ::"r"(d0),
-            "r"(a_lo), "r"(b0_lo), "r"(idesc0), "r"(accumulate), "r"(0x40004040u)
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+            "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
             : "memory");
     }
 }
@@ -411,18 +300,45 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                  : "memory");
     return v;
 }
+// named barrier of `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// fused head: acc[c] += x[q] * W2[col0 + q][c] for the 32 columns of one accumulator chunk; W2 rows of HCP floats in
+// shared memory (every lane reads the same address: broadcast)
+template <int HCP, int NH>
+__device__ __forceinline__ void tc_head_accumulate(const float (&x)[32], const float* __restrict__ w_rows,
+                                                   float (&hacc)[NH]) {
+    static_assert(HCP <= NH, "head accumulators");
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+#pragma unroll
+        for (int g = 0; g < HCP / 4; ++g) {
+            const float4 w = *reinterpret_cast<const float4*>(w_rows + q * HCP + 4 * g);
+            hacc[4 * g + 0] = fmaf(x[q], w.x, hacc[4 * g + 0]);
+            hacc[4 * g + 1] = fmaf(x[q], w.y, hacc[4 * g + 1]);
+            hacc[4 * g + 2] = fmaf(x[q], w.z, hacc[4 * g + 2]);
+            hacc[4 * g + 3] = fmaf(x[q], w.w, hacc[4 * g + 3]);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------ kernel
 // N of the MMA instructions of one item: n_tile <= 256 -> one instruction; wider tiles -> TC_NSPLIT0 + the rest.
 __host__ __device__ __forceinline__ int tc_n_first(int n_tile) { return n_tile > 256 ? TC_NSPLIT0 : n_tile; }
 
 // KT = kernel volume of the map (27: k3 s1, 8: k2 s2 and its transpose, 1: identity / MinkowskiLinear)
-template <int KT>
+// ES = operand element size (2: bf16, 4: fp32 rows read as tf32); HEAD: fused second linear in the epilogue (K = 1)
+template <int KT, int ES, bool HEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spconv_tc(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
+    constexpr int CPC = 128 / ES;    // channels per 128-byte chunk
+    constexpr int EPP = 16 / ES;     // channels per 16-byte piece
+    constexpr int KSTEP = 32 / ES;   // channels per MMA (32 bytes of K)
 
     const int S = p.stages;
     const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
@@ -431,8 +347,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
-    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][epilogue staging 8 x 2 KB][barriers][tmem ptr]
-    uint32_t off = (uint32_t)(S * TC_GI) * stage_bytes;  // S stages of TC_GI items
+    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][head W2 Cout*head_cp][epilogue staging 8 x 2 KB]
+    //        [barriers][tmem ptr]
+    uint32_t off = (uint32_t)S * stage_bytes;
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
     off += TC_BM * KT * 4;
     off = (off + 15u) & ~15u;
@@ -440,6 +357,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     off += p.Cout * 4;
     float* shift_s = reinterpret_cast<float*>(sm + off);
     off += p.Cout * 4;
+    off = (off + 15u) & ~15u;
+    float* head_w_s = reinterpret_cast<float*>(sm + off);
+    off += (uint32_t)(HEAD ? p.Cout * p.head_cp * 4 : 0);
     off = (off + 15u) & ~15u;
     const uint32_t stage_out = base + off;
     off += TC_EPI_WARPS * TC_STAGE_OUT_BYTES;
@@ -453,8 +373,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     off += 8;
     const uint32_t bar_tmem_full = base + off;   // [2] one per accumulator buffer
     off += 16;
-    const uint32_t bar_tmem_empty = base + off;  // [2]
-    off += 16;
+    const uint32_t bar_tmem_empty = base + off;  // [3] accumulator buffers / (256-column part, 128-column regions 0, 1)
+    off += 24;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + off);
 
     // ---- one-time setup
@@ -467,10 +387,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         }
         mbar_init(bar_nbr_full, 2);            // 2 prefetch warps
         mbar_init(bar_nbr_empty, 4);           // 4 producer warps
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_tmem_full + 8 * b, 1);                  // tcgen05.commit (multicast from the leader)
+        for (int b = 0; b < 2; ++b) mbar_init(bar_tmem_full + 8 * b, 1);  // tcgen05.commit (multicast from the leader)
+        for (int b = 0; b < 3; ++b)
             mbar_init(bar_tmem_empty + 8 * b, 2 * TC_EPI_WARPS);  // epilogue warps of both CTAs (leader's barrier)
-        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -484,18 +403,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         scale_s[i] = p.scale ? p.scale[i] : 1.f;
         shift_s[i] = p.shift ? p.shift[i] : 0.f;
     }
+    if (HEAD)
+        for (int i = tid; i < p.Cout * p.head_cp; i += TC_THREADS) head_w_s[i] = __ldg(p.head_w + i);
     tc_fence_before();
     cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     const int nchunk = p.nchunk1 + p.nchunk2;
     const int G = gridDim.x >> 1;          // clusters
-    const int unit0 = blockIdx.x >> 1;     // this cluster's first work item
+    const int unit0 = blockIdx.x >> 1;     // this cluster's first tile pair
+    const int NT = p.n_ntiles;
+    // work item `it` of this cluster = (tile pair unit0 + (it / NT) G, n-tile it % NT): the n-tiles of a tile pair run
+    // back to back on one cluster (its A rows are re-read from L2; the fused head sums over them in registers)
+    auto item_pair = [&](int it) -> int { return unit0 + (it / NT) * G; };
     // offsets (bit k) that at least one row of a 256-row tile pair needs: precomputed per map (b2me_tc_tile_masks),
     // so every role knows a tile's item list without waiting for the kernel-map rows
-    auto tile_mask = [&](int w) -> uint32_t {
+    auto pair_mask = [&](int tp) -> uint32_t {
         if (!p.tile_masks) return 1u;
-        const uint32_t m = __ldg(p.tile_masks + w / p.n_ntiles);
+        const uint32_t m = __ldg(p.tile_masks + tp);
         return m ? m : 1u;
     };
 
@@ -506,11 +431,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // absent neighbours = row -1 = out of bounds = zeros) from shfl-broadcast, i.e. warp-uniform, operands, so each
         // UTMALDG takes its operands from uniform registers without a per-lane serialisation loop.
         const uint32_t full_leader = mapa_u32(bar_full, 0u);
-        int ist = 0, iph = 0, it = 0;
-        uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.total_work ? tile_mask(unit0) : 0u, 0);
-        for (int w = unit0; w < p.total_work; w += G, ++it) {
+        int ist = 0, iph = 0;
+        uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.n_pairs ? pair_mask(unit0) : 0u, 0);
+        for (int it = 0;; ++it) {
+            if (item_pair(it) >= p.n_pairs) break;
             const uint32_t kmask = kmask_next;
-            if (w + G < p.total_work) kmask_next = __shfl_sync(0xffffffffu, tile_mask(w + G), 0);
+            const int tpn = item_pair(it + 1);
+            if (tpn < p.n_pairs) kmask_next = __shfl_sync(0xffffffffu, pair_mask(tpn), 0);
             mbar_wait(bar_nbr_full, (uint32_t)it & 1u);
 #pragma unroll 1
             for (uint32_t m = kmask; m; m &= m - 1u) {
@@ -528,8 +455,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     const int k2 = __ffs((int)m2) - 1;
                     const int id2 = nbr_s[(32 * warp + lane) * KT + k2];
                     if (id2 >= 0) {
-                        for (int ch = 0; ch < p.nchunk1; ++ch) prefetch_l2(p.in1 + (long long)id2 * p.Cin1 + ch * TC_BK);
-                        for (int ch = 0; ch < p.nchunk2; ++ch) prefetch_l2(p.in2 + (long long)id2 * p.Cin2 + ch * TC_BK);
+                        for (int ch = 0; ch < p.nchunk1; ++ch)
+                            prefetch_l2(p.in1 + ((long long)id2 * p.Cin1 + ch * CPC) * ES);
+                        for (int ch = 0; ch < p.nchunk2; ++ch)
+                            prefetch_l2(p.in2 + ((long long)id2 * p.Cin2 + ch * CPC) * ES);
                     }
                 }
 #pragma unroll 1
@@ -538,7 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     if (tc_elect_one()) {
                         const uint32_t a_s = base + (uint32_t)ist * stage_bytes + (uint32_t)(32 * warp) * 128u;
                         const CUtensorMap* tm = c < p.nchunk1 ? &p.tm_in1 : &p.tm_in2;
-                        const int col = (c < p.nchunk1 ? c : c - p.nchunk1) * TC_BK;
+                        const int col = (c < p.nchunk1 ? c : c - p.nchunk1) * CPC;
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
                             tma_gather4_pair(a_s + (uint32_t)g * 512u, tm, col, ids[4 * g], ids[4 * g + 1],
@@ -553,16 +482,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // =============================== gather producers ===============================
         const int j = tid & 7;        // 16-byte piece inside the 128-byte row
         const int rbase = tid >> 3;   // rows rbase + 16*i
-        int ist = 0, iph = 0;         // stage / phase of the next group of items to issue
-        int isub = 0;                 // item slot inside the group (a stage holds TC_GI items)
-        int it = 0;
+        int ist = 0, iph = 0;         // stage / phase of the next item to issue
         PROF_DECL
         const long long t_role0 = clock64();
         (void)t_role0;
-        uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
-        for (int w = unit0; w < p.total_work; w += G, ++it) {
+        uint32_t kmask_next = unit0 < p.n_pairs ? pair_mask(unit0) : 0u;
+        for (int it = 0;; ++it) {
+            if (item_pair(it) >= p.n_pairs) break;
             const uint32_t kmask = kmask_next;
-            if (w + G < p.total_work) kmask_next = tile_mask(w + G);
+            const int tpn = item_pair(it + 1);
+            if (tpn < p.n_pairs) kmask_next = pair_mask(tpn);
             PROF(1, mbar_wait(bar_nbr_full, (uint32_t)it & 1u));
 #pragma unroll 1
             for (int k = 0; k < KT; ++k) {
@@ -573,51 +502,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH && j < nchunk) {
+                } else if (TC_L2_PREFETCH) {
                     // the gathered rows come from all over the tensor (DRAM latency >> the ring's depth in time): pull
                     // the rows of the NEXT offset into L2 now, one whole offset (= nchunk items) ahead of their gather.
-                    // lane j takes the 128-byte chunk j of each of this thread's 8 rows.
+                    // lane j takes the 128-byte chunks j, j + 8, ... of each of this thread's 8 rows.
                     const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
-                    const __nv_bfloat16* psrc;
-                    int pcin, pcoff;
-                    if (j < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = j * TC_BK; }
-                    else { psrc = p.in2; pcin = p.Cin2; pcoff = (j - p.nchunk1) * TC_BK; }
+                    for (int cj = j; cj < nchunk; cj += 8) {
+                        const uint8_t* psrc;
+                        int pcin, pcoff;
+                        if (cj < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = cj * CPC; }
+                        else { psrc = p.in2; pcin = p.Cin2; pcoff = (cj - p.nchunk1) * CPC; }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int id = nbr_s[(rbase + 16 * i) * KT + k2];
-                        if (id >= 0) prefetch_l2(psrc + (long long)id * pcin + pcoff);
+                        for (int i = 0; i < 8; ++i) {
+                            const int id = nbr_s[(rbase + 16 * i) * KT + k2];
+                            if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
+                        }
                     }
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
-                    if (isub == 0) {
-                        PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
-                        PROF_COUNT(7);
-                    }
-                    const __nv_bfloat16* src;
+                    PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
+                    PROF_COUNT(7);
+                    const uint8_t* src;
                     int cin, coff;
-                    if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * TC_BK; }
-                    else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * TC_BK; }
-                    const int kw = min(TC_BK, cin - coff);
-                    if (j * 8 < kw && !(p.debug & 1)) {
-                        const uint32_t a_s = base + (uint32_t)(ist * TC_GI + isub) * stage_bytes;
+                    if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * CPC; }
+                    else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * CPC; }
+                    const int kw = min(CPC, cin - coff);
+                    if (j * EPP < kw && !(p.debug & 1)) {
+                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = rbase + 16 * i;
                             const uint32_t dst = a_s + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
                             const int id = idx[i];
-                            const __nv_bfloat16* g = src + (id >= 0 ? ((long long)id * cin + coff + j * 8) : 0);
+                            const uint8_t* g = src + (id >= 0 ? ((long long)id * cin + coff + j * EPP) * ES : 0);
                             cp_async_16(dst, g, id >= 0 ? 16u : 0u);
                         }
                     }
-                    const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
-                    if (++isub == TC_GI || tile_last) {
-                        // asynchronous publication: this thread's arrival fires when its copies have landed, so the
-                        // producers run ahead as far as the ring allows and never wait for their own gathers
-                        cp_async_mbar_arrive_noinc(bar_full + 8 * ist);
-                        isub = 0;
-                        if (++ist == S) { ist = 0; iph ^= 1; }
-                    }
+                    // asynchronous publication: this thread's arrival fires when its copies have landed, so the
+                    // producers run ahead as far as the ring allows and never wait for their own gathers
+                    cp_async_mbar_arrive_noinc(bar_full + 8 * ist);
+                    if (++ist == S) { ist = 0; iph ^= 1; }
                 }
             }
         }
@@ -627,48 +552,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
 #endif
     } else if (warp == 4) {
         // =============================== MMA issuer (leader) / stage relay (peer) ===============================
-        // The whole warp walks the item list and waits on the barriers; lane 0 alone issues the tcgen05 instructions
+        // The whole warp walks the item list and waits on the barriers; one elected lane issues the tcgen05 instructions
         // (measured: a wait executed by a lone lane of a divergent warp costs ~210 cycles even on a complete phase).
         if (rank == 0) {
-            // The whole warp walks the item list with warp-uniform values; every tcgen05 instruction sits in an asm
-            // block that elects the issuing lane itself (elect.sync), so the compiler emits ELECT + predicated
-            // UTCHMMA instead of a per-lane serialisation loop: ~90 instead of ~300 SASS instructions per item. The
-            // tensor pipe queues only a couple of MMAs, so every cycle of issue overhead beyond that slack idles it.
+            // Every value below is warp-uniform (shfl-broadcast or derived from kernel parameters), so the compiler
+            // keeps stage index, phase and descriptors in uniform registers and emits the UTCHMMA of an item back to
+            // back. The tensor pipe queues only a couple of MMAs, so every cycle of issue overhead idles it.
             const int n_a = tc_n_first(p.n_tile), n_b = p.n_tile - n_a;  // N of the one or two MMAs per K step
-            // kind::f16, bf16 x bf16 -> f32, K-major A and B, M = 256 (cta_group::2); each CTA's smem holds N/2 rows
-            const uint32_t idesc_a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_a >> 3) << 17) | (16u << 24);
-            const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_b >> 3) << 17) | (16u << 24);
-            // K steps (16 channels) of a full chunk and of the last chunk of each source
-            const int ks_last1 = (p.Cin1 - (p.nchunk1 - 1) * TC_BK) / 16;
-            const int ks_last2 = p.nchunk2 ? (p.Cin2 - (p.nchunk2 - 1) * TC_BK) / 16 : 0;
-            // low words of the SWIZZLE_128B K-major descriptors of stage 0 (high word is constant, see tc_kstep)
+            // operands K-major, fp32 accumulate, M = 256 (cta_group::2); each CTA's smem holds N/2 rows of B
+            constexpr uint32_t FMT = ES == 2 ? 1u : 2u;  // 1 = bf16, 2 = tf32
+            const uint32_t idesc_a = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(n_a >> 3) << 17) | (16u << 24);
+            const uint32_t idesc_b = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(n_b >> 3) << 17) | (16u << 24);
+            // K steps (32 bytes of K) of a full chunk and of the last chunk of each source
+            const int ks_last1 = (p.Cin1 - (p.nchunk1 - 1) * CPC) / KSTEP;
+            const int ks_last2 = p.nchunk2 ? (p.Cin2 - (p.nchunk2 - 1) * CPC) / KSTEP : 0;
+            // low words of the SWIZZLE_128B K-major descriptors of stage 0 (high word is constant, see tc_mma_lo)
             const uint32_t a_lo0 = ((base >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t stage_lo = stage_bytes >> 4;
             const uint32_t b_off_lo = TC_A_BYTES >> 4, b2_off_lo = (TC_A_BYTES + (uint32_t)(n_a >> 1) * 128u) >> 4;
             const bool need_fence = !p.tma;  // cp.async (generic proxy) writes of A -> visible to the MMA (async proxy)
-            int st = 0, ph = 0, it = 0;
+            int st = 0, ph = 0;
             PROF_DECL
             const long long t_role0 = clock64();
             (void)t_role0;
-            // shfl-broadcast values are warp-uniform to the compiler: with the tile masks and the TMEM base uniform, the
-            // whole loop (stage index, phase, descriptors) is computed on the uniform datapath
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.total_work ? tile_mask(unit0) : 0u, 0);
-            for (int w = unit0; w < p.total_work; w += G, ++it) {
+            uint32_t kmask_next = __shfl_sync(0xffffffffu, unit0 < p.n_pairs ? pair_mask(unit0) : 0u, 0);
+            for (int it = 0;; ++it) {
+                if (item_pair(it) >= p.n_pairs) break;
                 const uint32_t kmask = kmask_next;
-                if (w + G < p.total_work) kmask_next = __shfl_sync(0xffffffffu, tile_mask(w + G), 0);
-                // accumulator buffer of this work item and how often it has been used before
-                const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
-                const int au = p.acc_bufs == 2 ? (it >> 1) : it;
-                const uint32_t tmem_acc = tmem_u + (uint32_t)(ab * p.n_tile);
-                if (au > 0) {  // both CTAs' epilogues must have drained the previous tile of this buffer
-                    PROF(2, mbar_wait(bar_tmem_empty + 8 * ab, (uint32_t)(au - 1) & 1u));
-                    tc_fence_after();
+                const int tpn = item_pair(it + 1);
+                if (tpn < p.n_pairs) kmask_next = __shfl_sync(0xffffffffu, pair_mask(tpn), 0);
+                uint32_t tmem_acc, tmem_acc_b;  // columns of the first / second MMA of a K step
+                int fb;                         // tmem_full barrier of this item
+                if (p.rot128) {
+                    // 256-column part: one region, free once the previous tile's epilogue has read it; 128-column
+                    // part: region (it & 1), free once the epilogue of tile it - 2 has read it
+                    tmem_acc = tmem_u;
+                    tmem_acc_b = tmem_u + 256u + 128u * (uint32_t)(it & 1);
+                    fb = 0;
+                    if (it >= 1) PROF(2, mbar_wait(bar_tmem_empty, (uint32_t)(it - 1) & 1u));
+                    if (it >= 2) PROF(2, mbar_wait(bar_tmem_empty + 8 * (1 + (it & 1)), (uint32_t)((it >> 1) - 1) & 1u));
+                } else {
+                    // accumulator buffer of this work item and how often it has been used before
+                    const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
+                    const int au = p.acc_bufs == 2 ? (it >> 1) : it;
+                    tmem_acc = tmem_u + (uint32_t)(ab * p.n_tile);
+                    tmem_acc_b = tmem_acc + (uint32_t)n_a;
+                    fb = ab;
+                    if (au > 0)  // both CTAs' epilogues must have drained the previous tile of this buffer
+                        PROF(2, mbar_wait(bar_tmem_empty + 8 * ab, (uint32_t)(au - 1) & 1u));
                 }
+                tc_fence_after();
                 uint32_t acc = 0u;
                 for (uint32_t m = kmask; m; m &= m - 1u) {  // one pass per kernel offset the tile needs
                     for (int c = 0; c < nchunk; ++c) {
-                        int ks = (c == p.nchunk1 - 1) ? ks_last1 : ((c == nchunk - 1) ? ks_last2 : TC_BK / 16);
+                        int ks = (c == p.nchunk1 - 1) ? ks_last1 : ((c == nchunk - 1) ? ks_last2 : 4);
 #ifdef B2ME_TC_PROFILE
                         if (p.debug & 4) ks = 0;
 #endif
@@ -680,18 +618,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         tc_fence_after();
                         const uint32_t a_lo = a_lo0 + (uint32_t)st * stage_lo;
                         if (tc_elect_one()) {
-#if defined(B2ME_TC_PROFILE) || defined(B2ME_TC_EXPERIMENT)
-                            if (need_fence && !(p.debug & 8)) fence_proxy_async();  // 8: timing experiment only
-#else
                             if (need_fence) fence_proxy_async();
-#endif
                             // the two instructions of a K step share the A slice; both read it from shared memory
                             // (keeping it in the collector buffer, collector::a::fill / lastuse, was measured slower)
                             for (int kk = 0; kk < ks; ++kk) {
-                                tc_mma_lo(tmem_acc, a_lo + 2u * kk, a_lo + b_off_lo + 2u * kk, idesc_a, acc);
+                                tc_mma_lo<ES>(tmem_acc, a_lo + 2u * kk, a_lo + b_off_lo + 2u * kk, idesc_a, acc);
                                 if (n_b)
-                                    tc_mma_lo(tmem_acc + (uint32_t)n_a, a_lo + 2u * kk, a_lo + b2_off_lo + 2u * kk,
-                                              idesc_b, acc);
+                                    tc_mma_lo<ES>(tmem_acc_b, a_lo + 2u * kk, a_lo + b2_off_lo + 2u * kk, idesc_b, acc);
                                 acc = 1u;
                             }
                             tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
@@ -704,7 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
 #endif
                     }
                 }
-                tc_commit_pair_elect(bar_tmem_full + 8 * ab);  // accumulators of both CTAs are complete
+                tc_commit_pair_elect(bar_tmem_full + 8 * fb);  // accumulators of both CTAs are complete
             }
 #ifdef B2ME_TC_PROFILE
             prof_[0] = (unsigned long long)(clock64() - t_role0);
@@ -717,26 +650,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             PROF_DECL
             const long long t_role0 = clock64();
             (void)t_role0;
-            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
-            for (int w = unit0; w < p.total_work; w += G) {
+            uint32_t kmask_next = unit0 < p.n_pairs ? pair_mask(unit0) : 0u;
+            for (int it = 0;; ++it) {
+                if (item_pair(it) >= p.n_pairs) break;
                 const uint32_t kmask = kmask_next;
-                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
-                int sub = 0;
-                for (int k = 0; k < KT; ++k) {
-                    if (!((kmask >> k) & 1u)) continue;
-                    for (int c = 0; c < nchunk; ++c) {
-                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
-                        if (++sub < TC_GI && !tile_last) continue;
-                        sub = 0;
-                        PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
-                        PROF_COUNT(7);
-                        if (lane == 0) {
-                            fence_proxy_async();
-                            mbar_arrive_remote(bar_full + 8 * st, 0u);
-                        }
-                        __syncwarp();
-                        if (++st == S) { st = 0; ph ^= 1; }
+                const int tpn = item_pair(it + 1);
+                if (tpn < p.n_pairs) kmask_next = pair_mask(tpn);
+                const int items = __popc(kmask) * nchunk;
+                for (int q = 0; q < items; ++q) {
+                    PROF(3, mbar_wait(bar_full + 8 * st, (uint32_t)ph));
+                    PROF_COUNT(7);
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_arrive_remote(bar_full + 8 * st, 0u);
                     }
+                    __syncwarp();
+                    if (++st == S) { st = 0; ph ^= 1; }
                 }
             }
 #ifdef B2ME_TC_PROFILE
@@ -746,57 +675,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         }
     } else if (warp == 5) {
         // =============================== weight (B) loader ===============================
-        {
-            int st = 0, ph = 0;
-            const uint32_t full_leader = mapa_u32(bar_full, 0u);
-            uint32_t kmask_next = unit0 < p.total_work ? tile_mask(unit0) : 0u;
-            for (int w = unit0; w < p.total_work; w += G) {
-                const uint32_t kmask = kmask_next;
-                if (w + G < p.total_work) kmask_next = tile_mask(w + G);
-                const int nt = w % p.n_ntiles;
-                int sub = 0;
-                for (int k = 0; k < KT; ++k) {
-                    if (!((kmask >> k) & 1u)) continue;
-                    for (int c = 0; c < nchunk; ++c) {
-                        const bool tile_last = ((kmask >> k) == 1u) && (c == nchunk - 1);
-                        if (sub == 0) mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
-                        if (lane == 0) {
-                            const uint32_t b_s = base + (uint32_t)(st * TC_GI + sub) * stage_bytes + TC_A_BYTES;
-                            const uint8_t* g =
-                                p.wpacked + ((((size_t)nt * KT + k) * nchunk + c) * 2 + rank) * (size_t)p.b_bytes;
-                            if (p.tma) {
-                                // leader: one arrive announcing all four transfers of the stage (A and B of both CTAs)
-                                if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * st, 2u * (TC_A_BYTES + p.b_bytes));
-                                const long long item = ((long long)nt * KT + k) * nchunk + c;
-                                tma_load_2d_pair(b_s, &p.tm_w, 0, (int)((item * 2 + rank) * (p.n_tile / 2)),
-                                                 full_leader + 8 * st);
-                            } else if (p.debug & 2) {
-                                if (sub == 0) mbar_arrive(bar_full + 8 * st);
-                            } else {
-                                // one arrive per group, announcing the bytes of all its items (1 or TC_GI)
-                                if (sub == 0)
-                                    mbar_arrive_expect_tx(bar_full + 8 * st, tile_last ? p.b_bytes : TC_GI * p.b_bytes);
-                                bulk_copy_g2s(b_s, g, p.b_bytes, bar_full + 8 * st);
-                            }
-                        }
-                        if (++sub == TC_GI || tile_last) {
-                            __syncwarp();
-                            sub = 0;
-                            if (++st == S) { st = 0; ph ^= 1; }
+        int st = 0, ph = 0;
+        const uint32_t full_leader = mapa_u32(bar_full, 0u);
+        uint32_t kmask_next = unit0 < p.n_pairs ? pair_mask(unit0) : 0u;
+        for (int it = 0;; ++it) {
+            if (item_pair(it) >= p.n_pairs) break;
+            const uint32_t kmask = kmask_next;
+            const int tpn = item_pair(it + 1);
+            if (tpn < p.n_pairs) kmask_next = pair_mask(tpn);
+            const int nt = it % NT;
+            for (int k = 0; k < KT; ++k) {
+                if (!((kmask >> k) & 1u)) continue;
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
+                    if (lane == 0) {
+                        const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
+                        const long long item = ((long long)nt * KT + k) * nchunk + c;
+                        if (p.tma) {
+                            // leader: one arrive announcing all four transfers of the stage (A and B of both CTAs)
+                            if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * st, 2u * (TC_A_BYTES + p.b_bytes));
+                            tma_load_2d_pair(b_s, &p.tm_w, 0, (int)((item * 2 + rank) * (p.n_tile / 2)),
+                                             full_leader + 8 * st);
+                        } else if (p.debug & 2) {
+                            mbar_arrive(bar_full + 8 * st);
+                        } else {
+                            mbar_arrive_expect_tx(bar_full + 8 * st, p.b_bytes);
+                            bulk_copy_g2s(b_s, p.wpacked + (size_t)(item * 2 + rank) * (size_t)p.b_bytes, p.b_bytes,
+                                          bar_full + 8 * st);
                         }
                     }
+                    __syncwarp();
+                    if (++st == S) { st = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp < 8) {
         // =============================== kernel-map prefetch ===============================
-        // warp wl stages rows 64 wl .. 64 wl + 63 of every tile: 64 x KT entries, 2 KT per lane, held in registers
-        // until the producers have released the (single) smem buffer.
+        // warp wl stages rows 64 wl .. 64 wl + 63 of every item's tile: 64 x KT entries, 2 KT per lane, held in
+        // registers until the producers have released the (single) smem buffer.
         const int wl = warp - 6;
         constexpr int NJ = 2 * KT;
-        int it = 0;
-        for (int w = unit0; w < p.total_work; w += G, ++it) {
-            const long long row0 = ((long long)(w / p.n_ntiles) * 2 + rank) * TC_BM + 64 * wl;
+        for (int it = 0;; ++it) {
+            const int tp = item_pair(it);
+            if (tp >= p.n_pairs) break;
+            const long long row0 = ((long long)tp * 2 + rank) * TC_BM + 64 * wl;
             int rowreg[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -833,29 +755,147 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         const uint32_t own = stg + (uint32_t)lane * 64u;
         const int own_sw = (lane >> 1) & 3;
         const int crow = lane >> 2, cq = lane & 3;  // coalesced view: rows crow + 8 m, piece cq
-        // this warp's columns: 32-column chunks [c_lo, c_hi) of the tile
-        const int nch = (p.n_tile + 31) >> 5;
-        const int c_lo = chalf ? ((nch + 1) >> 1) * 32 : 0;
-        const int c_hi = chalf ? p.n_tile : min(p.n_tile, ((nch + 1) >> 1) * 32);
-        int it = 0;
+        // this warp's columns: up to two runs of 32-column chunks, [s0_lo, s0_hi) then [s1_lo, s1_hi)
+        int s0_lo, s0_hi, s1_lo, s1_hi;
+        if (p.rot128) {  // n_tile = 384: its half of the 256-column part first, then its half of the 128-column part
+            s0_lo = chalf ? 128 : 0;   s0_hi = s0_lo + 128;
+            s1_lo = chalf ? 320 : 256; s1_hi = s1_lo + 64;
+        } else {
+            const int nch = (p.n_tile + 31) >> 5;
+            s0_lo = chalf ? ((nch + 1) >> 1) * 32 : 0;
+            s0_hi = chalf ? p.n_tile : min(p.n_tile, ((nch + 1) >> 1) * 32);
+            s1_lo = s1_hi = 0;
+        }
+        const int n_s0 = s0_hi > s0_lo ? (s0_hi - s0_lo + 31) >> 5 : 0;
+        const int n_s1 = s1_hi > s1_lo ? (s1_hi - s1_lo + 31) >> 5 : 0;
+        const int n_my = n_s0 + n_s1;                       // chunks of this warp per item
+        auto chunk_col = [&](int ci) -> int { return ci < n_s0 ? s0_lo + 32 * ci : s1_lo + 32 * (ci - n_s0); };
+        float hacc[HEAD ? TC_HEAD_MAX : 1];  // fused head: partial logits of this lane's row over this warp's columns
+#pragma unroll
+        for (int c = 0; c < (HEAD ? TC_HEAD_MAX : 1); ++c) hacc[c] = 0.f;
         PROF_DECL
-        for (int w = unit0; w < p.total_work; w += G, ++it) {
-            const int tile_p = w / p.n_ntiles;
-            const int n0 = (w - tile_p * p.n_ntiles) * p.n_tile;
-            const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
-            const uint32_t au_par = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it) & 1u;
-            const uint32_t lane_addr = lane_addr0 + (uint32_t)(ab * p.n_tile);
-            const uint32_t bar_tf = bar_tmem_full + 8 * ab, bar_te = bar_tmem_empty + 8 * ab;
+        for (int it = 0;; ++it) {
+            const int tile_p = item_pair(it);
+            if (tile_p >= p.n_pairs) break;
+            const int nt = it % NT;
+            const int n0 = nt * p.n_tile;
+            // accumulator columns / barriers of this item (see the MMA warp)
+            uint32_t lane_addr, col_b_off;
+            uint32_t bar_tf, bar_te_a, bar_te_b, tf_par;
+            if (p.rot128) {
+                lane_addr = lane_addr0;
+                col_b_off = 128u * (uint32_t)(it & 1);   // TMEM column of tile column c >= 256: c + col_b_off
+                bar_tf = bar_tmem_full;
+                tf_par = (uint32_t)it & 1u;
+                bar_te_a = bar_tmem_empty;
+                bar_te_b = bar_tmem_empty + 8 * (1 + (it & 1));
+            } else {
+                const int ab = p.acc_bufs == 2 ? (it & 1) : 0;
+                lane_addr = lane_addr0 + (uint32_t)(ab * p.n_tile);
+                col_b_off = 0u;
+                bar_tf = bar_tmem_full + 8 * ab;
+                tf_par = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it) & 1u;
+                bar_te_a = bar_te_b = bar_tmem_empty + 8 * ab;
+            }
+            auto tmem_col = [&](int cb) -> uint32_t { return lane_addr + (uint32_t)cb + (cb >= 256 ? col_b_off : 0u); };
+            // release of the accumulator part(s) after chunk ci of this warp has been read out of TMEM
+            auto release_after = [&](int ci) {
+                const bool last = ci == n_my - 1;
+                const bool last_a = p.rot128 && ci == n_s0 - 1;
+                if (last || last_a) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(last ? bar_te_b : bar_te_a, 0u);  // the leader's barrier
+                }
+            };
             const long long slot = ((long long)tile_p * 2 + rank) * TC_BM + we * 32 + lane;
             const int row = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
-            int crows[4];  // output rows of the coalesced view
-#pragma unroll
-            for (int m = 0; m < 4; ++m) crows[m] = __shfl_sync(0xffffffffu, row, crow + 8 * m);
 
-            if (p.out_dtype == B2ME_BF16) {
-                const __nv_bfloat16* resp = p.residual;
+            if constexpr (HEAD) {
+                // ---------------- fused head: hidden activation -> partial logits, nothing of the tile is stored
+                PROF(1, mbar_wait(bar_tf, tf_par));
+                tc_fence_after();
+                if (n_my == 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
+                }
+                for (int ci = 0; ci < n_my; ++ci) {
+                    const int cb = chunk_col(ci);
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem_col(cb), r);  // head mode: n_tile % 64 == 0, every chunk is 32 columns wide
+                    tmem_ld_wait();
+                    release_after(ci);
+                    float x[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const int col = n0 + cb + q4 * 4;
+                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
+                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                        x[q4 * 4 + 0] = apply_act(__uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x, p.act, p.slope);
+                        x[q4 * 4 + 1] = apply_act(__uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y, p.act, p.slope);
+                        x[q4 * 4 + 2] = apply_act(__uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z, p.act, p.slope);
+                        x[q4 * 4 + 3] = apply_act(__uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w, p.act, p.slope);
+                    }
+                    // the hidden activation is a bf16 (tf32-rounded fp32) tensor in the unfused data path: same rounding
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        x[q] = ES == 2 ? __bfloat162float(__float2bfloat16_rn(x[q])) : round_tf32(x[q]);
+                    const float* w_rows = head_w_s + (n0 + cb) * p.head_cp;
+                    switch (p.head_cp) {
+                        case 4: tc_head_accumulate<4>(x, w_rows, hacc); break;
+                        case 8: tc_head_accumulate<8>(x, w_rows, hacc); break;
+                        case 12: tc_head_accumulate<12>(x, w_rows, hacc); break;
+                        default: tc_head_accumulate<16>(x, w_rows, hacc); break;
+                    }
+                }
+                if (nt == NT - 1) {
+                    // combine the two column halves of every row: the upper-half warp hands its sums over through its
+                    // staging block, the lower-half warp adds (fixed order: lower + upper + bias), stores, arg-maxes
+                    if (chalf == 1) {
+#pragma unroll
+                        for (int g = 0; g < TC_HEAD_MAX / 4; ++g)
+                            st_shared_v4(own + 16u * g, make_uint4(__float_as_uint(hacc[4 * g]), __float_as_uint(hacc[4 * g + 1]),
+                                                                  __float_as_uint(hacc[4 * g + 2]), __float_as_uint(hacc[4 * g + 3])));
+                    }
+                    named_bar_sync(1 + we, 64);
+                    if (chalf == 0) {
+                        const uint32_t partner = stage_out + (uint32_t)(ew + 4) * TC_STAGE_OUT_BYTES + (uint32_t)lane * 64u;
+                        float tot[TC_HEAD_MAX];
+#pragma unroll
+                        for (int g = 0; g < TC_HEAD_MAX / 4; ++g) {
+                            const uint4 o = ld_shared_v4(partner + 16u * g);
+                            tot[4 * g + 0] = hacc[4 * g + 0] + __uint_as_float(o.x);
+                            tot[4 * g + 1] = hacc[4 * g + 1] + __uint_as_float(o.y);
+                            tot[4 * g + 2] = hacc[4 * g + 2] + __uint_as_float(o.z);
+                            tot[4 * g + 3] = hacc[4 * g + 3] + __uint_as_float(o.w);
+                        }
+                        if (row >= 0) {
+                            float best = -INFINITY;
+                            int besti = 0;
+#pragma unroll
+                            for (int c = 0; c < TC_HEAD_MAX; ++c) {
+                                if (c < p.head_c) {
+                                    const float v = tot[c] + (p.head_b ? __ldg(p.head_b + c) : 0.f);
+                                    p.head_logits[(long long)row * p.head_c + c] = v;
+                                    if (v > best) {  // strict: lowest index wins ties (torch.max semantics)
+                                        best = v;
+                                        besti = c;
+                                    }
+                                }
+                            }
+                            if (p.head_argmax) p.head_argmax[row] = (uint8_t)besti;
+                        }
+                    }
+                    named_bar_sync(1 + we, 64);  // the staging block may be rewritten
+#pragma unroll
+                    for (int c = 0; c < TC_HEAD_MAX; ++c) hacc[c] = 0.f;
+                }
+            } else if (ES == 2 && p.out_dtype == B2ME_BF16) {
+                int crows[4];  // output rows of the coalesced view
+#pragma unroll
+                for (int m = 0; m < 4; ++m) crows[m] = __shfl_sync(0xffffffffu, row, crow + 8 * m);
+                const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.residual);
                 __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-#if TC_EPI_STAGED
                 uint4 R[4];
                 auto load_res = [&](int cb) {  // coalesced: 64-byte segment of 8 rows per access
                     const int cw = min(32, p.n_tile - cb);
@@ -867,23 +907,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                                                                         cq * 8));
                     }
                 };
-                if (resp && c_lo < c_hi) load_res(c_lo);
-                PROF(1, mbar_wait(bar_tf, au_par));
+                if (resp && n_my > 0) load_res(chunk_col(0));
+                PROF(1, mbar_wait(bar_tf, tf_par));
                 tc_fence_after();
 #ifdef B2ME_TC_PROFILE
                 const long long t_epi0 = clock64();
 #endif
-                if (c_lo >= c_hi) {  // narrow tile: this warp has no columns
+                if (n_my == 0) {  // narrow tile: this warp has no columns
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
+                    if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
-                for (int cb = c_lo; cb < c_hi; cb += 32) {
+                for (int ci = 0; ci < n_my; ++ci) {
+                    const int cb = chunk_col(ci);
                     const int cw = min(32, p.n_tile - cb);
                     uint32_t r[32];
                     if (cw == 32) {
-                        tmem_ld_x32(lane_addr + (uint32_t)cb, r);
+                        tmem_ld_x32(tmem_col(cb), r);
                     } else {
-                        tmem_ld_x16(lane_addr + (uint32_t)cb, r);
+                        tmem_ld_x16(tmem_col(cb), r);
 #pragma unroll
                         for (int q = 16; q < 32; ++q) r[q] = 0u;
                     }
@@ -894,14 +935,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             st_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4), R[m]);
                         }
                         __syncwarp();
-                        if (cb + 32 < c_hi) load_res(cb + 32);  // in flight during this chunk's math and stores
+                        if (ci + 1 < n_my) load_res(chunk_col(ci + 1));  // in flight during this chunk's math and stores
                     }
                     tmem_ld_wait();
-                    if (cb + 32 >= c_hi) {  // this warp's part of the accumulator is read: release it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);  // the leader's barrier
-                    }
+                    release_after(ci);  // this warp's part of the accumulator (region) is read: release it
                     float v[32];
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
@@ -948,101 +985,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     }
                     __syncwarp();  // staging is reused by the next chunk
                 }
-#else
-                uint4 R[4];
-                // row-per-lane epilogue (TC_EPI_STAGED 0): every lane loads / stores the 64 contiguous bytes of ITS row per
-                // 32-column chunk, no shared-memory round trip. Measured 10-60 % SLOWER than the staged variant (32
-                // half-used sectors per store instruction), kept for experiments only.
-                const long long rbase_o = (long long)(row >= 0 ? row : 0) * p.Cout + n0;
-                auto load_res = [&](int cb) {
-                    const int cw = min(32, p.n_tile - cb);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        R[m] = make_uint4(0u, 0u, 0u, 0u);
-                        if (row >= 0 && m * 8 < cw)
-                            R[m] = __ldg(reinterpret_cast<const uint4*>(resp + rbase_o + cb + m * 8));
-                    }
-                };
-                if (resp && c_lo < c_hi) load_res(c_lo);
-                PROF(1, mbar_wait(bar_tf, au_par));
-                tc_fence_after();
-#ifdef B2ME_TC_PROFILE
-                const long long t_epi0 = clock64();
-#endif
-                if (c_lo >= c_hi) {  // narrow tile: this warp has no columns
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
-                }
-                for (int cb = c_lo; cb < c_hi; cb += 32) {
-                    const int cw = min(32, p.n_tile - cb);
-                    uint32_t r[32];
-                    if (cw == 32) {
-                        tmem_ld_x32(lane_addr + (uint32_t)cb, r);
-                    } else {
-                        tmem_ld_x16(lane_addr + (uint32_t)cb, r);
-#pragma unroll
-                        for (int q = 16; q < 32; ++q) r[q] = 0u;
-                    }
-                    uint4 Rc[4];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) Rc[m] = R[m];
-                    if (resp && cb + 32 < c_hi) load_res(cb + 32);  // in flight during this chunk's math and stores
-                    tmem_ld_wait();
-                    if (cb + 32 >= c_hi) {  // this warp's part of the accumulator is read: release it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);  // the leader's barrier
-                    }
-                    float v[32];
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
-                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
-                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
-                        v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
-                        v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
-                        v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
-                        v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
-                    }
-                    if (resp) {
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const uint32_t wv[4] = {Rc[q4].x, Rc[q4].y, Rc[q4].z, Rc[q4].w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
-                                v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint32_t wv[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float x0 = apply_act(v[q4 * 8 + 2 * e], p.act, p.slope);
-                            const float x1 = apply_act(v[q4 * 8 + 2 * e + 1], p.act, p.slope);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                            wv[e] = *reinterpret_cast<uint32_t*>(&h);
-                        }
-                        if (row >= 0 && q4 * 8 < cw)
-                            *reinterpret_cast<uint4*>(outp + rbase_o + cb + q4 * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                    }
-                }
-#endif
 #ifdef B2ME_TC_PROFILE
                 prof_[2] += (unsigned long long)(clock64() - t_epi0);
                 ++prof_[7];
 #endif
             } else {
-                // fp32 rows (parity tests only): row-per-lane stores, 16-column chunks split between the two halves
-                mbar_wait(bar_tf, au_par);
+                // fp32 rows (tf32 mode; bf16 parity tests): row-per-lane stores of 16-column chunks split between the
+                // two column halves. B2ME_TF32: the stored values are rounded to tf32 (they feed the next tf32 MMA).
+                mbar_wait(bar_tf, tf_par);
                 tc_fence_after();
                 const int n16 = p.n_tile >> 4;
                 const int q_lo = chalf ? (n16 + 1) >> 1 : 0, q_hi = chalf ? n16 : (n16 + 1) >> 1;
                 if (q_lo >= q_hi) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_te, 0u);
+                    if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
                 for (int qc = q_lo; qc < q_hi; ++qc) {
                     const int cb = qc * 16;
@@ -1052,7 +1008,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     if (qc + 1 >= q_hi) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_te, 0u);
+                        if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                     }
                     if (row < 0) continue;
                     float v[16];
@@ -1061,21 +1017,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         v[q] = __uint_as_float(r[q]) * scale_s[n0 + cb + q] + shift_s[n0 + cb + q];
                     const long long o = (long long)row * p.Cout + n0 + cb;
                     if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + o);
-                        const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-                        const uint32_t wv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                        if (ES == 4) {
+                            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            v[2 * q] += __uint_as_float(wv[q] << 16);
-                            v[2 * q + 1] += __uint_as_float(wv[q] & 0xFFFF0000u);
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 ra = __ldg(rp + q);
+                                v[4 * q] += ra.x; v[4 * q + 1] += ra.y; v[4 * q + 2] += ra.z; v[4 * q + 3] += ra.w;
+                            }
+                        } else {
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + o);
+                            const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                            const uint32_t wv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                v[2 * q] += __uint_as_float(wv[q] << 16);
+                                v[2 * q + 1] += __uint_as_float(wv[q] & 0xFFFF0000u);
+                            }
                         }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        v[q] = apply_act(v[q], p.act, p.slope);
+                        if (p.out_dtype == B2ME_TF32) v[q] = round_tf32(v[q]);
                     }
                     float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        op[q] = make_float4(apply_act(v[4 * q], p.act, p.slope), apply_act(v[4 * q + 1], p.act, p.slope),
-                                            apply_act(v[4 * q + 2], p.act, p.slope),
-                                            apply_act(v[4 * q + 3], p.act, p.slope));
+                    for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
             }
         }
@@ -1142,6 +1109,7 @@ static int tc_n_tile(int K, int Cout) {
     if (Cout % 128 == 0) return 128;
     return Cout <= 384 ? Cout : 0;
 }
+static int tc_elem_size(int op_dtype) { return op_dtype == B2ME_BF16 ? 2 : (op_dtype == B2ME_TF32 ? 4 : 0); }
 
 extern "C" int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout) {
     if ((K != 1 && K != 8 && K != 27) || Cin1 < 16 || Cin2 < 0 || Cout < 16 || Cout > 1024) return 0;
@@ -1152,15 +1120,19 @@ extern "C" int b2me_tc_supported(int K, int Cin1, int Cin2, int Cout) {
     return 1;
 }
 
-extern "C" size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout) {
-    if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return 0;
-    const int nchunk = (Cin1 + TC_BK - 1) / TC_BK + (Cin2 + TC_BK - 1) / TC_BK;
+extern "C" size_t b2me_tc_packed_bytes(int K, int Cin1, int Cin2, int Cout, int op_dtype) {
+    const int es = tc_elem_size(op_dtype);
+    if (!es || !b2me_tc_supported(K, Cin1, Cin2, Cout)) return 0;
+    const int cpc = 128 / es;
+    const int nchunk = (Cin1 + cpc - 1) / cpc + (Cin2 + cpc - 1) / cpc;
     return (size_t)K * nchunk * (size_t)Cout * 128;
 }
 
 // one thread per 16-byte piece of the packed image
+template <int ES>
 __global__ void k_tc_pack(const float* __restrict__ W, int K, int Cin1, int Cin2, int Cout, int n_tile, int nchunk1,
                           int nchunk2, uint4* __restrict__ packed, long long total_pieces) {
+    constexpr int CPC = 128 / ES, EPP = 16 / ES;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_pieces) return;
     const int nchunk = nchunk1 + nchunk2;
@@ -1173,20 +1145,25 @@ __global__ void k_tc_pack(const float* __restrict__ W, int K, int Cin1, int Cin2
     const int k = (int)(rest % K);
     const int nt = (int)(rest / K);
     int cin_base, cin_end;
-    if (c < nchunk1) { cin_base = c * TC_BK; cin_end = Cin1; }
-    else { cin_base = Cin1 + (c - nchunk1) * TC_BK; cin_end = Cin1 + Cin2; }
+    if (c < nchunk1) { cin_base = c * CPC; cin_end = Cin1; }
+    else { cin_base = Cin1 + (c - nchunk1) * CPC; cin_end = Cin1 + Cin2; }
     const int Cin = Cin1 + Cin2;
+    float f[EPP];
+#pragma unroll
+    for (int e = 0; e < EPP; ++e) {
+        const int cin = cin_base + j * EPP + e;
+        f[e] = (cin < cin_end) ? W[((long long)k * Cin + cin) * Cout + (nt * n_tile + n)] : 0.f;
+    }
     uint32_t w[4];
+    if (ES == 2) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        float f[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int cin = cin_base + j * 8 + e * 2 + h;
-            f[h] = (cin < cin_end) ? W[((long long)k * Cin + cin) * Cout + (nt * n_tile + n)] : 0.f;
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(f[(2 * e) % EPP], f[(2 * e + 1) % EPP]);
+            w[e] = *reinterpret_cast<uint32_t*>(&v);
         }
-        __nv_bfloat162 v = __floats2bfloat162_rn(f[0], f[1]);
-        w[e] = *reinterpret_cast<uint32_t*>(&v);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(round_tf32(f[e % EPP]));
     }
     // image of one item = [cta rank 0 | cta rank 1]; a CTA's part = its half of the rows of each of the (one or two)
     // MMA instructions of a K step: instruction a covers columns [0, n_a), instruction b covers [n_a, n_tile)
@@ -1202,30 +1179,37 @@ __global__ void k_tc_pack(const float* __restrict__ W, int K, int Cin1, int Cin2
     packed[piece] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-extern "C" int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, void* packed,
+extern "C" int b2me_tc_pack_weights(const float* W, int K, int Cin1, int Cin2, int Cout, int op_dtype, void* packed,
                                     b2me_stream_t stream) {
     if (!W || !packed) return B2ME_EINVAL;
-    if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
+    const int es = tc_elem_size(op_dtype);
+    if (!es || !b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
     const int nt = tc_n_tile(K, Cout);
-    const int nchunk1 = (Cin1 + TC_BK - 1) / TC_BK, nchunk2 = (Cin2 + TC_BK - 1) / TC_BK;
+    const int cpc = 128 / es;
+    const int nchunk1 = (Cin1 + cpc - 1) / cpc, nchunk2 = (Cin2 + cpc - 1) / cpc;
     const long long total = (long long)(Cout / nt) * K * (nchunk1 + nchunk2) * nt * 8;
-    k_tc_pack<<<(unsigned)ceil_div64(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        W, K, Cin1, Cin2, Cout, nt, nchunk1, nchunk2, reinterpret_cast<uint4*>(packed), total);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (es == 2)
+        k_tc_pack<2><<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(W, K, Cin1, Cin2, Cout, nt, nchunk1, nchunk2,
+                                                                     reinterpret_cast<uint4*>(packed), total);
+    else
+        k_tc_pack<4><<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(W, K, Cin1, Cin2, Cout, nt, nchunk1, nchunk2,
+                                                                     reinterpret_cast<uint4*>(packed), total);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
 
+// SM count of the CURRENT device (one cached entry per device ordinal; a process may drive several GPUs)
 static int tc_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            sms = n;
-        else
-            sms = B2ME_NUM_SMS;
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B2ME_NUM_SMS;
+    if (!sms[dev]) {
+        int n = 0;
+        sms[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+                       ? n : B2ME_NUM_SMS;
     }
-    return sms;
+    return sms[dev];
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
@@ -1233,7 +1217,7 @@ typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, 
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static tc_encode_fn tc_encoder() {
-    static tc_encode_fn fn = nullptr;
+    static tc_encode_fn fn = nullptr;  // a process-wide function pointer of the driver, not a per-device fact
     static bool tried = false;
     if (!tried) {
         tried = true;
@@ -1245,67 +1229,83 @@ static tc_encode_fn tc_encoder() {
     }
     return fn;
 }
-// 2-D bf16 tensor [rows, cols] (row pitch = cols), box = box_cols x box_rows
-static bool tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+// 2-D tensor [rows, cols] of es-byte elements (row pitch = cols), box = box_cols x box_rows
+static bool tc_make_map(CUtensorMap* tm, const void* base, int es, uint64_t rows, uint64_t cols, uint32_t box_cols,
                         uint32_t box_rows, CUtensorMapSwizzle swz) {
     tc_encode_fn enc = tc_encoder();
-    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || (cols * 2) % 16) return false;
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || (cols * es) % 16) return false;
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint64_t strides[1] = {cols * es};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (enc(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     return true;
 }
 
-template <int KT>
+template <int KT, int ES, bool HEAD>
 static int tc_launch(const TcParams& p, size_t smem, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_spconv_tc<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) !=
-            cudaSuccess)
-            return B2ME_ELAUNCH;
-        attr_set = true;
-    }
-    const int clusters = p.total_work < tc_num_sms() / 2 ? p.total_work : tc_num_sms() / 2;
-    k_spconv_tc<KT><<<2 * clusters, TC_THREADS, smem, stream>>>(p);  // __cluster_dims__(2,1,1): CTA pairs
+    // per-device function attribute: set on every launch (cheap), so a process that drives several GPUs works
+    if (cudaFuncSetAttribute(k_spconv_tc<KT, ES, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) !=
+        cudaSuccess)
+        return B2ME_ELAUNCH;
+    const int half = tc_num_sms() / 2;
+    const int clusters = p.n_pairs < half ? p.n_pairs : half;
+    k_spconv_tc<KT, ES, HEAD><<<2 * clusters, TC_THREADS, smem, stream>>>(p);  // __cluster_dims__(2,1,1): CTA pairs
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
 
-extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in,
-                                  const void* packed_w,
-                                  const int32_t* nbr, const int32_t* perm, const uint32_t* tile_masks, int K,
-                                  int64_t V_out, int Cout,
-                                  const float* scale, const float* shift, const void* residual, int act, float slope,
-                                  void* out, int out_dtype, b2me_stream_t stream) {
-    if (!in1 || !packed_w || !out || V_out < 0 || V_in < 0) return B2ME_EINVAL;
+struct TcHead {
+    const float* w;
+    const float* b;
+    int c;
+    float* logits;
+    uint8_t* argmax;
+};
+
+static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in, int op_dtype, const void* packed_w,
+                  const int32_t* nbr, const int32_t* perm, const uint32_t* tile_masks, int K, int64_t V_out, int Cout,
+                  const float* scale, const float* shift, const void* residual, int act, float slope, void* out,
+                  int out_dtype, const TcHead* head, int flags, b2me_stream_t stream) {
+    const int es = tc_elem_size(op_dtype);
+    if (!es) return B2ME_EINVAL;
+    if (!in1 || !packed_w || V_out < 0 || V_in < 0) return B2ME_EINVAL;
+    if (!head && !out) return B2ME_EINVAL;
     if (Cin2 > 0 && !in2) return B2ME_EINVAL;
     if (!nbr && K != 1) return B2ME_EINVAL;
     if (nbr && !tile_masks) return B2ME_EINVAL;
     if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
-    if (out_dtype != B2ME_BF16 && out_dtype != B2ME_F32) return B2ME_EINVAL;
+    if (!head) {
+        if (es == 2 && out_dtype != B2ME_BF16 && out_dtype != B2ME_F32) return B2ME_EINVAL;
+        if (es == 4 && out_dtype != B2ME_TF32 && out_dtype != B2ME_F32) return B2ME_EINVAL;
+    }
     if (V_out == 0) return B2ME_OK;
 
     TcParams p;
-    p.in1 = reinterpret_cast<const __nv_bfloat16*>(in1);
-    p.in2 = reinterpret_cast<const __nv_bfloat16*>(in2);
+    const int cpc = 128 / es;
+    p.in1 = reinterpret_cast<const uint8_t*>(in1);
+    p.in2 = reinterpret_cast<const uint8_t*>(in2);
     p.wpacked = reinterpret_cast<const uint8_t*>(packed_w);
     p.nbr = nbr;
     p.perm = perm;
     p.tile_masks = nbr ? tile_masks : nullptr;
     p.scale = scale;
     p.shift = shift;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    p.residual = residual;
     p.out = out;
+    p.head_w = nullptr;
+    p.head_b = nullptr;
+    p.head_logits = nullptr;
+    p.head_argmax = nullptr;
+    p.head_c = p.head_cp = 0;
     p.V_out = V_out;
     p.Cin1 = Cin1;
     p.Cin2 = Cin2;
-    p.nchunk1 = (Cin1 + TC_BK - 1) / TC_BK;
-    p.nchunk2 = (Cin2 + TC_BK - 1) / TC_BK;
+    p.nchunk1 = (Cin1 + cpc - 1) / cpc;
+    p.nchunk2 = (Cin2 + cpc - 1) / cpc;
     p.Cout = Cout;
     p.n_tile = tc_n_tile(K, Cout);
     p.n_ntiles = Cout / p.n_tile;
@@ -1314,16 +1314,31 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     p.slope = slope;
     p.b_bytes = (unsigned)(p.n_tile / 2) * 128u;  // each CTA of the pair stages half of every weight tile
     p.acc_bufs = 2 * p.n_tile <= 512 ? 2 : 1;
+    size_t head_bytes = 0;
+    if (head) {
+        if (!head->w || !head->logits || head->c < 1 || head->c > TC_HEAD_MAX || p.n_tile % 64 || residual)
+            return B2ME_EINVAL;
+        p.head_w = head->w;
+        p.head_b = head->b;
+        p.head_logits = head->logits;
+        p.head_argmax = head->argmax;
+        p.head_c = head->c;
+        p.head_cp = (head->c + 3) / 4 * 4;
+        head_bytes = (size_t)Cout * p.head_cp * 4;
+    }
+    // n_tile = 256 + 128 with bf16 rows out: early release of the 256-column part + alternating 128-column regions
+    p.rot128 = (!head && p.n_tile == 384 && TC_NSPLIT0 == 256 && out_dtype == B2ME_BF16 &&
+                !(flags & B2ME_TC_FLAG_NO_ROT128)) ? 1 : 0;
     int cols = 32;
-    while (cols < p.acc_bufs * p.n_tile) cols <<= 1;
+    while (cols < (p.rot128 ? 512 : p.acc_bufs * p.n_tile)) cols <<= 1;
     p.tmem_cols = cols;
-    const int64_t work = ceil_div64(V_out, 2 * TC_BM) * p.n_ntiles;  // 256-row tile pairs x n-tiles
-    if (work > 0x7fffffff) return B2ME_EUNSUPPORTED;
-    p.total_work = (int)work;
+    const int64_t pairs = ceil_div64(V_out, 2 * TC_BM);  // 256-row tile pairs
+    if (pairs * p.n_ntiles > 0x7fffffff) return B2ME_EUNSUPPORTED;
+    p.n_pairs = (int)pairs;
 
-    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 +
-                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 6 * 8 + 16;
-    const size_t stage_bytes = (size_t)TC_GI * (TC_A_BYTES + p.b_bytes);  // a stage holds TC_GI items
+    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 + head_bytes + 16 +
+                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 16 + 16 + 24 + 16;
+    const size_t stage_bytes = (size_t)TC_A_BYTES + p.b_bytes;
     int S = TC_MAX_STAGES;
     while (S >= 2 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
     if (S < 2) return B2ME_EUNSUPPORTED;
@@ -1336,24 +1351,20 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     }
 #endif
     p.stages = S;
-    // B2ME_TC_TMA=1 routes the operands through the TMA unit (tile::gather4 rows + 2-D weight boxes completing on the
-    // leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
-    // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms once the 8 UTMALDG per warp and item
-    // issue from uniform registers; whole step 232.2 vs 231.1 ms), so it stays an opt-in alternative that the parity
-    // tests also cover.
-    static int want_tma = -1;
-    if (want_tma < 0) {
-        const char* e = getenv("B2ME_TC_TMA");
-        want_tma = (e && atoi(e) == 1) ? 1 : 0;
-    }
+    // B2ME_TC_FLAG_TMA routes the operands through the TMA unit (tile::gather4 rows + 2-D weight boxes completing on
+    // the leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
+    // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms), so it is an alternative the caller picks
+    // per call; the parity tests run both.
     p.tma = 0;
-    if (want_tma && TC_GI == 1 && V_in > 0) {
+    if ((flags & B2ME_TC_FLAG_TMA) && V_in > 0) {
         const uint64_t w_rows = (uint64_t)K * (p.nchunk1 + p.nchunk2) * (uint64_t)Cout;
-        bool ok = tc_make_map(&p.tm_in1, in1, (uint64_t)V_in, (uint64_t)Cin1, TC_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+        bool ok = tc_make_map(&p.tm_in1, in1, es, (uint64_t)V_in, (uint64_t)Cin1, (uint32_t)cpc, 1,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
         if (ok && Cin2 > 0)
-            ok = tc_make_map(&p.tm_in2, in2, (uint64_t)V_in, (uint64_t)Cin2, TC_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (ok)
-            ok = tc_make_map(&p.tm_w, packed_w, w_rows, 64, 64, (uint32_t)(p.n_tile / 2), CU_TENSOR_MAP_SWIZZLE_NONE);
+            ok = tc_make_map(&p.tm_in2, in2, es, (uint64_t)V_in, (uint64_t)Cin2, (uint32_t)cpc, 1,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ok)  // the packed image as rows of 64 two-byte words = 128 bytes, whatever the operand type
+            ok = tc_make_map(&p.tm_w, packed_w, 2, w_rows, 64, 64, (uint32_t)(p.n_tile / 2), CU_TENSOR_MAP_SWIZZLE_NONE);
         if (!ok) return B2ME_ELAUNCH;
         p.tma = 1;
     }
@@ -1361,8 +1372,35 @@ extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, in
     if (smem < TC_MIN_SMEM) smem = TC_MIN_SMEM;
 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (K == 27) return tc_launch<27>(p, smem, s);
-    if (K == 8) return tc_launch<8>(p, smem, s);
-    if (K == 1) return tc_launch<1>(p, smem, s);
+    if (head) return es == 2 ? tc_launch<1, 2, true>(p, smem, s) : tc_launch<1, 4, true>(p, smem, s);
+    if (es == 2) {
+        if (K == 27) return tc_launch<27, 2, false>(p, smem, s);
+        if (K == 8) return tc_launch<8, 2, false>(p, smem, s);
+        if (K == 1) return tc_launch<1, 2, false>(p, smem, s);
+    } else {
+        if (K == 27) return tc_launch<27, 4, false>(p, smem, s);
+        if (K == 8) return tc_launch<8, 4, false>(p, smem, s);
+        if (K == 1) return tc_launch<1, 4, false>(p, smem, s);
+    }
     return B2ME_EUNSUPPORTED;
+}
+
+extern "C" int b2me_spconv_fwd_tc(const void* in1, int Cin1, const void* in2, int Cin2, int64_t V_in, int op_dtype,
+                                  const void* packed_w,
+                                  const int32_t* nbr, const int32_t* perm, const uint32_t* tile_masks, int K,
+                                  int64_t V_out, int Cout,
+                                  const float* scale, const float* shift, const void* residual, int act, float slope,
+                                  void* out, int out_dtype, int flags, b2me_stream_t stream) {
+    return tc_run(in1, Cin1, in2, Cin2, V_in, op_dtype, packed_w, nbr, perm, tile_masks, K, V_out, Cout, scale, shift,
+                  residual, act, slope, out, out_dtype, nullptr, flags, stream);
+}
+
+extern "C" int b2me_head_fused_tc(const void* in, int Cin, int64_t V, int op_dtype, const void* packed_w1, int Chid,
+                                  const float* scale1, const float* shift1, int act1, float slope1,
+                                  const float* W2p, const float* b2, int C2, float* out_logits, uint8_t* out_argmax,
+                                  int flags, b2me_stream_t stream) {
+    if (!out_logits || !W2p) return B2ME_EINVAL;
+    TcHead h{W2p, b2, C2, out_logits, out_argmax};
+    return tc_run(in, Cin, nullptr, 0, V, op_dtype, packed_w1, nullptr, nullptr, nullptr, 1, V, Chid, scale1, shift1,
+                  nullptr, act1, slope1, nullptr, B2ME_F32, &h, flags, stream);
 }

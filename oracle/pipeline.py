@@ -29,11 +29,24 @@ DEFAULTS = dict(seg_scale=200.0, rot_scale=200.0, kp_scale=800.0, ee_point_count
 
 
 def normalize_colors(rgb_input):
-    """utils/preprocess.py:20-37 (the min-max branch for negative inputs is not reachable with valid colours)."""
+    """utils/preprocess.py:20-37: /255 when the maximum exceeds 2; per-channel min-max rescale to [0, 1] when a value
+    is negative (sklearn.preprocessing.minmax_scale: X * scale + min_ with scale = 1 / (max - min) in the input's
+    float32); - 0.5 when the result lies in [0, 1]."""
     rgb = np.array(rgb_input, copy=True)
-    if rgb.size and rgb.max() > 2:
+    if not rgb.size:
+        return rgb
+    if rgb.max() > 2:
         rgb /= 255.0
-    if rgb.size and rgb.min() > (-1e-6) and rgb.max() < (1 + 1e-6):
+    if rgb.min() < 0:
+        for c in range(3):
+            col = rgb[:, c]
+            lo, hi = col.min(), col.max()
+            rng = hi - lo
+            scale = (np.float32(1.0) / (rng if rng != 0 else np.float32(1.0))).astype(rgb.dtype)
+            min_ = (0 - lo * scale).astype(rgb.dtype)
+            col *= scale
+            col += min_
+    if rgb.min() > (-1e-6) and rgb.max() < (1 + 1e-6):
         rgb -= 0.5
     return rgb
 
@@ -58,7 +71,8 @@ def predict_segmentation(seg_model, points, rgb_norm, scale, cluster_dist=0.06):
     out = seg_model(fld.sparse()).slice(fld)
     seg = og.segmentation_labels(out.F).astype(np.int64)
     top2 = out.F.float().topk(2, dim=1)[0]
-    raw = dict(labels=seg.copy(), margin=(top2[:, 0] - top2[:, 1]).numpy(), scale=float(out.F.abs().max()))
+    raw = dict(labels=seg.copy(), margin=(top2[:, 0] - top2[:, 1]).numpy(), scale=float(out.F.abs().max()),
+               point_logits=out.F.float().numpy())
     ee_idx = np.where(seg == 2)[0]
     seg[ee_idx] = 1
     if len(ee_idx) > 1:

@@ -91,6 +91,15 @@ def main():
     c, off = P.center_at_origin(pts)
     out.update(pre_pts=pts, pre_centered=c, pre_offset=off, pre_rgb255=rgb255, pre_rgb255_out=P.normalize_colors(rgb255),
                pre_rgb01=rgb01, pre_rgb01_out=P.normalize_colors(rgb01))
+    # the "negative input" branch (per-channel min-max rescale, utils/preprocess.py:28-32) and already-centred input;
+    # own generator so that the entries recorded before these were added keep their values
+    rng2 = np.random.default_rng(99)
+    rgbneg = (rng2.random((400, 3)) * 1.5 - 0.3).astype(np.float32)
+    rgbcen = (rng2.random((400, 3)) - 0.5).astype(np.float32)
+    rgbneg255 = (rng2.random((400, 3)) * 300 - 20).astype(np.float32)
+    out.update(pre_rgbneg=rgbneg, pre_rgbneg_out=P.normalize_colors(rgbneg), pre_rgbcen=rgbcen,
+               pre_rgbcen_out=P.normalize_colors(rgbcen), pre_rgbneg255=rgbneg255,
+               pre_rgbneg255_out=P.normalize_colors(rgbneg255))
     # ---- per-point heads: the reference's own utils/output.py (:45-87) and utils/metrics.py (:110-127), imported with
     #      this repo's oracle package standing in for `MinkowskiEngine` (output.py only uses it in a type annotation)
     import torch

@@ -108,6 +108,28 @@ def main():
         n_ee = int((r.segmentation == 2).sum())
         print(f"frame {i}: {len(f['points'])} points, {n_ee} EE points after the cluster filter, ee_pose",
               None if r.ee_pose is None else np.round(r.ee_pose, 4))
+        # voxel logits of the UNCHANGED reference RobotNetSegmentation on this frame, through the reference's own call
+        # pattern (app/inference_engine.py:405-417), and the raw 7-vector of the unchanged RobotNetEncode on the EE crop
+        # (app/inference_engine.py:437-457): what the CUDA package has to reproduce through the mirror model files
+        with torch.no_grad():
+            rgbn = torch.from_numpy(rgb255 / 255.0 - 0.5).to(torch.float32)
+            pts_t = torch.from_numpy(f["points"])
+            fld = OME.TensorField(features=rgbn, quantization_mode=OME.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE,
+                                  minkowski_algorithm=OME.MinkowskiAlgorithm.SPEED_OPTIMIZED,
+                                  coordinates=OME.utils.batched_coordinates([pts_t * cfg.INFERENCE.SEGMENTATION.scale],
+                                                                            dtype=torch.float32))
+            sout = seg(fld.sparse())
+            out[f"f{i}_voxel_coords"] = sout.C.numpy().astype(np.int32)
+            out[f"f{i}_voxel_logits"] = sout.F.numpy().astype(np.float32)
+            out[f"f{i}_point_labels_raw"] = sout.slice(fld).F.max(1)[1].numpy().astype(np.int8)
+            ee = np.where(r.segmentation == 2)[0]
+            ee_pts = f["points"][ee]
+            ee_pts = ee_pts - (ee_pts.max(0) + ee_pts.min(0)) / 2          # utils/preprocess.py:8-11
+            rfld = OME.TensorField(features=rgbn[ee], quantization_mode=OME.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE,
+                                   minkowski_algorithm=OME.MinkowskiAlgorithm.SPEED_OPTIMIZED,
+                                   coordinates=OME.utils.batched_coordinates(
+                                       [torch.from_numpy(ee_pts) * cfg.INFERENCE.ROTATION.scale], dtype=torch.float32))
+            out[f"f{i}_rot_out"] = rot(rfld.sparse())[0].numpy().astype(np.float32)
         out[f"f{i}_points"] = f["points"]
         out[f"f{i}_rgb255"] = rgb255
         out[f"f{i}_segmentation"] = r.segmentation.astype(np.int8)

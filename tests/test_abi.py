@@ -36,8 +36,9 @@ def test_sizes_without_gpu(built_lib):
     assert lib.b2me_tc_supported(27, 384, 32, 384) == 1
     assert lib.b2me_tc_supported(27, 3, 0, 32) == 0          # stem goes to the SIMT kernel
     assert lib.b2me_tc_supported(1, 1024, 0, 3) == 0
-    assert lib.b2me_tc_packed_bytes(27, 384, 32, 384) == 27 * 7 * 384 * 128
-    assert lib.b2me_tc_packed_bytes(1, 256, 0, 1024) == 4 * 1024 * 128
+    assert lib.b2me_tc_packed_bytes(27, 384, 32, 384, 1) == 27 * 7 * 384 * 128
+    assert lib.b2me_tc_packed_bytes(1, 256, 0, 1024, 1) == 4 * 1024 * 128
+    assert lib.b2me_tc_packed_bytes(27, 384, 32, 384, 2) == 27 * 13 * 384 * 128   # tf32: 32 channels per chunk
 
 
 def test_no_cpu_fallback(built_lib):

@@ -69,6 +69,24 @@ def test_sparse_tensor_int_coords_first_wins():
     assert torch.equal(c.C.cpu(), o.C) and torch.equal(c.F.cpu(), o.F)
 
 
+def test_sparse_collate_feeds_sparse_tensor():
+    """a4 -> a5, the reference's training / test call pattern (data/alivev2.py:386-396 then test.py:52
+    `ME.SparseTensor(feats, coordinates=coords, device=...)`): ragged samples with duplicates collated on the host,
+    voxelised on the GPU; coordinates and first-wins features bit-exact vs the oracle."""
+    ME = _cuda_me()
+    g = torch.Generator().manual_seed(4)
+    coords = [torch.randint(-9, 10, (n, 3), generator=g).float() + 0.25 for n in (3000, 0, 1700)]
+    feats = [torch.rand(len(c), 3, generator=g) for c in coords]
+    labels = [torch.randint(0, 3, (len(c),), generator=g) for c in coords]
+    cb, fb, lb = ME.utils.sparse_collate(coords, feats, labels, dtype=torch.float32)
+    ocb, ofb, olb = OME.utils.sparse_collate(coords, feats, labels, dtype=torch.float32)
+    assert torch.equal(cb, ocb) and torch.equal(fb, ofb) and torch.equal(lb, olb)
+    o = OME.SparseTensor(ofb, ocb)
+    c = ME.SparseTensor(fb, cb, device="cuda")
+    assert torch.equal(c.C.cpu(), o.C) and torch.equal(c.F.cpu(), o.F)
+    assert set(c.C[:, 0].cpu().tolist()) == {0, 2}        # the empty sample keeps its batch index free
+
+
 def test_stride_and_kernel_maps_bit_exact():
     ME = _cuda_me()
     pts = [kinect_like_cloud(40000, 21), kinect_like_cloud(30000, 22) - np.float32(1.0)]

@@ -133,3 +133,49 @@ def test_translation_magic_vs_reference_golden(golden):
     print("translation max abs err vs reference", err)
     assert err < 1e-4
     assert err < 2e-5
+
+
+def test_sanity_check_kernel_vs_reference_golden():
+    """b2me_sanity_check (on-device InferenceEngine.check_sanity, app/inference_engine.py:246-279 + utils/data.py:255-335
+    + utils/metrics.py:130-136) against the verdicts of the reference's OWN check_sanity on 24 seeded EE crops
+    (tests/golden/make_golden_sanity.py: both verdicts, every failure mode), all crops in one launch."""
+    import os
+    from conftest import GOLDEN
+    from b200calib.output import sanity_check_batched
+    g = np.load(os.path.join(GOLDEN, "reference_sanity.npz"))
+    S = len(g["sane"])
+    crops, offs, prob, xyz = [], [0], np.zeros((S, 6), np.float32), np.zeros((S, 6, 3), np.float32)
+    for c in range(S):
+        ee = g["points"][c][g["seg"][c] == 2]
+        crops.append(ee)
+        offs.append(offs[-1] + len(ee))
+        m = int(g["n_pred"][c])
+        for k, p in zip(g["pred_cls"][c][:m], g["pred_xyz"][c][:m]):
+            prob[c, int(k)] = 1.0
+            xyz[c, int(k)] = p
+    got = sanity_check_batched(torch.from_numpy(np.concatenate(crops)).cuda(), np.asarray(offs, np.int32),
+                               torch.from_numpy(g["pose"]), torch.from_numpy(prob), torch.from_numpy(xyz),
+                               kp_threshold=0.5).cpu().numpy().astype(bool)
+    assert np.array_equal(got, g["sane"]), np.nonzero(got != g["sane"])[0]
+    assert 5 < got.sum() < S - 5
+    # without key points only the point-count and corner tests apply (len(result.key_points) <= 3)
+    nokp = sanity_check_batched(torch.from_numpy(np.concatenate(crops)).cuda(), np.asarray(offs, np.int32),
+                                torch.from_numpy(g["pose"])).cpu().numpy().astype(bool)
+    from b200calib import sanity as HS
+    want = np.array([HS.check_sanity(g["points"][c], g["seg"][c].astype(np.int64), g["pose"][c], []) for c in range(S)])
+    assert np.array_equal(nokp, want)
+
+
+def test_normalize_colors_kernel_vs_reference_golden(golden):
+    """b2me_normalize_colors (utils/preprocess.py:20-37 per frame of a batch) against outputs of the reference's own
+    normalize_colors: 0..255 input, 0..1 input, negative inputs (per-channel min-max branch) and an already centred
+    input as FIVE FRAMES OF ONE BATCH (mixed ranges in one batch), bit-exact."""
+    from b200calib.output import normalize_colors_batched
+    keys = ["pre_rgb255", "pre_rgb01", "pre_rgbneg", "pre_rgbcen", "pre_rgbneg255"]
+    frames = [golden[k] for k in keys]
+    offs = np.concatenate(([0], np.cumsum([len(f) for f in frames]))).astype(np.int32)
+    bidx = np.repeat(np.arange(len(frames), dtype=np.float32), [len(f) for f in frames])
+    out = normalize_colors_batched(torch.from_numpy(np.concatenate(frames)).cuda(), torch.from_numpy(bidx).cuda(),
+                                   offs).cpu().numpy()
+    for i, k in enumerate(keys):
+        assert np.array_equal(out[offs[i]:offs[i + 1]], golden[k + "_out"]), k

@@ -42,7 +42,7 @@ def nets():
     return ME, o, c.cuda().eval()
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), ("tf32", 1e-3), (torch.bfloat16, 2e-2)])
 def test_segmentation_forward_parity(nets, dtype, tol):
     ME, onet, cnet = nets
     pts, rgb = zip(_frame(seed=13), _frame(seed=14))
@@ -62,6 +62,8 @@ def test_segmentation_forward_parity(nets, dtype, tol):
         noise = (pc - po).abs().max()
         decided = margin > 2 * noise
         assert torch.equal(lab_o[decided], lab_c[decided])
+        mism = int((lab_o != lab_c).sum())
+        print(f"labels ({dtype}): {mism} of {len(lab_o)} differ from the oracle (no mask)")
         if dtype == torch.float32:
             assert float(decided.float().mean()) > 0.99
             assert float((lab_o == lab_c).float().mean()) > 0.999
@@ -116,6 +118,29 @@ def test_lazy_fusion_launch_count(nets):
         cnet(x2).F
     # 49 convolutions + 2 head linears (maps cached): no separate BN / ReLU / add / cat kernels
     assert ME.launch_count() == 51
+    # tensor-core modes: the two head linears are ONE launch (b2me_head_fused_tc); + 1 conversion of the fp32 voxel
+    # features of the test's SparseTensor to the activation type... none: the stem runs on the SIMT kernel from fp32
+    for mode in ("bf16", "tf32"):
+        ME.set_compute_dtype(mode)
+        try:
+            with torch.no_grad():
+                cnet(x2).F           # packs the weights of this operand type
+                ME.reset_launch_count()
+                out = cnet(x2)
+                out.F
+            assert ME.launch_count() == 50, (mode, ME.launch_count())
+            assert getattr(out, "_row_argmax", None) is not None
+            ME.set_fuse_head(False)
+            with torch.no_grad():
+                ME.reset_launch_count()
+                two = cnet(x2)
+                two.F
+            assert ME.launch_count() == 51
+            assert float((two.F - out.F).abs().max()) <= 1e-5 * float(two.F.abs().max())
+            assert int((two._row_argmax != out._row_argmax).sum()) <= 1
+        finally:
+            ME.set_fuse_head(True)
+            ME.set_compute_dtype(torch.float32)
 
 
 def test_robotnet_full_unet_global_max_pool_parity(nets):

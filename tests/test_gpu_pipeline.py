@@ -165,6 +165,62 @@ def test_predict_batch_vs_reference_predict_golden():
             assert G.rotation_angle_deg(Tg[:3, :3], To[:3, :3]) < 0.01, (i, mine, gold)
 
 
+@pytest.mark.parametrize("mode,tol", [("f32", 1e-3), ("tf32", 1e-3), ("bf16", 2e-2)])
+def test_unchanged_reference_models_golden_logits(mode, tol):
+    """Voxel logits of the UNCHANGED reference classes model/robotnet_segmentation.py:RobotNetSegmentation and the raw
+    output of model/robotnet_encode.py:RobotNetEncode (run on the oracle package in the authoring container by
+    tests/golden/make_golden_predict.py, where /root/reference exists) against the CUDA package. The GPU box has no
+    /root/reference, so the networks are rebuilt from the recorded seeds through the mirror b200calib/models.py, whose
+    equality with the unchanged classes is pinned by weight sums here and by state-dict / output identity in
+    tests/test_models_vs_reference.py. Voxel coordinates bit-exact; logits within the north-star tolerance."""
+    import os
+    import MinkowskiEngine as ME
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "reference_predict.npz"))
+    M = make_models(ME)
+    torch.manual_seed(int(g["seed_seg"]))
+    seg = randomize_bn_stats(M.RobotNetSegmentation(3, num_classes=3), int(g["seed_seg"])).eval()
+    with torch.no_grad():
+        seg.regression[2].linear.bias.copy_(torch.from_numpy(g["seg_head_bias"]))
+    torch.manual_seed(int(g["seed_rot"]))
+    rot = randomize_bn_stats(M.RobotNetEncode(3, 7), int(g["seed_rot"])).eval()
+    ws = float(sum(v.double().abs().sum() for v in seg.state_dict().values()))
+    assert abs(ws - float(g["seg_weight_sum"])) < 1e-6 * ws
+    seg, rot = seg.cuda(), rot.cuda()
+    ME.set_compute_dtype(mode)
+    try:
+        for i in range(2):
+            pts = torch.from_numpy(g[f"f{i}_points"])
+            rgbn = torch.from_numpy(g[f"f{i}_rgb255"] / 255.0 - 0.5).to(torch.float32)
+            co = OME.utils.batched_coordinates([pts * float(g["seg_scale"])], dtype=torch.float32)
+            fld = ME.TensorField(features=rgbn, coordinates=co, device="cuda",
+                                 quantization_mode=ME.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE,
+                                 minkowski_algorithm=ME.MinkowskiAlgorithm.SPEED_OPTIMIZED)
+            with torch.no_grad():
+                out = seg(fld.sparse())
+            assert np.array_equal(out.C.cpu().numpy(), g[f"f{i}_voxel_coords"])
+            gold = torch.from_numpy(g[f"f{i}_voxel_logits"])
+            err = float((out.F.float().cpu().double() - gold.double()).norm() / gold.double().norm())
+            lab = out.slice(fld).F.float().cpu().max(1)[1].numpy()
+            mism = int((lab != g[f"f{i}_point_labels_raw"]).sum())
+            print(f"[{mode}] frame {i}: voxel logits rel err vs unchanged reference model {err:.2e}; "
+                  f"{mism} of {len(lab)} raw labels differ")
+            assert err < tol
+            assert mism <= {"f32": 1e-4, "tf32": 5e-3, "bf16": 5e-2}[mode] * len(lab) + 1
+            # rotation network on the EE crop the reference engine formed (labels == 2 of its final segmentation)
+            ee = np.where(g[f"f{i}_segmentation"] == 2)[0]
+            ee_pts = g[f"f{i}_points"][ee]
+            ee_pts = ee_pts - (ee_pts.max(0) + ee_pts.min(0)) / 2
+            rco = OME.utils.batched_coordinates([torch.from_numpy(ee_pts) * float(g["rot_scale"])], dtype=torch.float32)
+            rfld = ME.TensorField(features=rgbn[ee], coordinates=rco, device="cuda",
+                                  quantization_mode=ME.SparseTensorQuantizationMode.UNWEIGHTED_AVERAGE)
+            with torch.no_grad():
+                ro = rot(rfld.sparse())[0].float().cpu().numpy()
+            assert np.abs(ro - g[f"f{i}_rot_out"]).max() < (3e-2 if mode == "bf16" else 2e-4), (ro, g[f"f{i}_rot_out"])
+    finally:
+        ME.set_compute_dtype(torch.float32)
+
+
 def test_predict_batch_sanity_check_wiring(setup):
     """PipelineConfig.sanity_check: is_confident is check_sanity (b200calib/sanity.py, pinned by the reference's own
     outputs in tests/test_sanity_golden.py) of the frame's points, the crop labels, the EE pose before ICP and the

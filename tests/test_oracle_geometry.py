@@ -52,6 +52,8 @@ def test_preprocess_vs_reference_golden(golden):
     assert np.array_equal(c, golden["pre_centered"]) and np.array_equal(off, golden["pre_offset"])
     assert np.array_equal(OP.normalize_colors(golden["pre_rgb255"]), golden["pre_rgb255_out"])
     assert np.array_equal(OP.normalize_colors(golden["pre_rgb01"]), golden["pre_rgb01_out"])
+    for k in ("pre_rgbneg", "pre_rgbcen", "pre_rgbneg255"):     # negative inputs: per-channel min-max branch
+        assert np.array_equal(OP.normalize_colors(golden[k]), golden[k + "_out"]), k
 
 
 def test_largest_cluster_vs_sklearn():

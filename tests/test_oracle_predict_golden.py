@@ -43,3 +43,21 @@ def test_oracle_pipeline_vs_reference_predict_golden():
         assert np.allclose(r["ee_pose"][:3], ee[:3], atol=1e-6) and np.allclose(r["ee_pose"][3:], ee[3:], atol=1e-6)
         assert np.allclose(r["base_pose"][:3], base[:3], atol=1e-6)
         assert min(np.abs(r["base_pose"][3:] - base[3:]).max(), np.abs(r["base_pose"][3:] + base[3:]).max()) < 1e-6
+
+
+def test_mirror_models_reproduce_unchanged_reference_logits():
+    """b200calib/models.py (the mirror the GPU box runs) against the UNCHANGED reference classes on the same substrate
+    (the oracle package): voxel coordinates and voxel logits of RobotNetSegmentation and the raw RobotNetEncode output
+    recorded by make_golden_predict.py are reproduced to fp32 round-off - the mirror IS the reference topology."""
+    g = np.load(os.path.join(GOLDEN, "reference_predict.npz"))
+    seg, rot = _nets(g)
+    for i in range(2):
+        pts = torch.from_numpy(g[f"f{i}_points"])
+        rgbn = torch.from_numpy(g[f"f{i}_rgb255"] / 255.0 - 0.5).to(torch.float32)
+        fld = OME.TensorField(features=rgbn, coordinates=OME.utils.batched_coordinates([pts * float(g["seg_scale"])],
+                                                                                     dtype=torch.float32))
+        with torch.no_grad():
+            out = seg(fld.sparse())
+        assert np.array_equal(out.C.numpy(), g[f"f{i}_voxel_coords"])
+        assert np.allclose(out.F.numpy(), g[f"f{i}_voxel_logits"], rtol=0, atol=1e-6)
+        assert np.array_equal(out.slice(fld).F.max(1)[1].numpy(), g[f"f{i}_point_labels_raw"])

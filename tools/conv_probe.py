@@ -27,9 +27,16 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--level", type=int, default=1, help="tensor stride of the map (1 or 2)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--path", default="cpasync", choices=["cpasync", "tma"], help="operand path (B2ME_TC_FLAG_TMA)")
+    ap.add_argument("--no-rot128", action="store_true", help="384-column tiles: single accumulator (round-1 layout)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--head", type=int, default=0, help="K=1 shapes: time the fused head with this many classes instead")
     a = ap.parse_args()
     import MinkowskiEngine as ME
-    from MinkowskiEngine._lib import lib, ptr, stream, check, BF16
+    from MinkowskiEngine._lib import lib, ptr, stream, check, BF16, TF32, TC_FLAG_TMA, TC_FLAG_NO_ROT128
+    op = TF32 if a.dtype == "tf32" else BF16
+    flags = (TC_FLAG_TMA if a.path == "tma" else 0) | (TC_FLAG_NO_ROT128 if a.no_rot128 else 0)
+    adt = torch.float32 if a.dtype == "tf32" else torch.bfloat16
     from b200calib.synthetic import make_frame
     frames = [make_frame(13000 + i) for i in range(a.frames)]
     pts = torch.from_numpy(np.concatenate([f["points"] for f in frames])).cuda()
@@ -54,10 +61,10 @@ def main():
     for spec in a.shapes.split(","):
         K, cin, cout = [int(x) for x in spec.split(":")]
         g = torch.Generator(device="cuda").manual_seed(1)
-        x = torch.randn(V, cin, device="cuda", generator=g).bfloat16()
+        x = torch.randn(V, cin, device="cuda", generator=g).to(adt)
         W = (torch.randn(K, cin, cout, device="cuda", generator=g) / np.sqrt(K * cin)).contiguous()
-        packed = torch.empty(lib.b2me_tc_packed_bytes(K, cin, 0, cout), dtype=torch.uint8, device="cuda")
-        check(lib.b2me_tc_pack_weights(ptr(W), K, cin, 0, cout, ptr(packed), stream()))
+        packed = torch.empty(lib.b2me_tc_packed_bytes(K, cin, 0, cout, op), dtype=torch.uint8, device="cuda")
+        check(lib.b2me_tc_pack_weights(ptr(W), K, cin, 0, cout, op, ptr(packed), stream()))
         if K == 27:
             nbr, perm, masks = nbr27, perm27, masks27
         elif K == 8:
@@ -66,12 +73,22 @@ def main():
             perm, masks = mgr.perm_stride(rec, "up")
         else:
             nbr, perm, masks = None, None, None
-        out = torch.empty(V, cout, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(V, cout, device="cuda", dtype=adt)
+        head = a.head if (K == 1 and a.head) else 0
+        if head:
+            W2p = torch.randn(cout, (head + 3) // 4 * 4, device="cuda", generator=g)
+            logits = torch.empty(V, head, device="cuda")
+            amax = torch.empty(V, dtype=torch.uint8, device="cuda")
         pairs = int((nbr >= 0).sum()) if nbr is not None else V
 
         def run():
-            check(lib.b2me_spconv_fwd_tc(ptr(x), cin, None, 0, x.shape[0], ptr(packed), ptr(nbr), ptr(perm), ptr(masks), K, V, cout,
-                                         None, None, None, 1, 0.0, ptr(out), BF16, stream()))
+            if head:
+                check(lib.b2me_head_fused_tc(ptr(x), cin, V, op, ptr(packed), cout, None, None, 2, 0.01, ptr(W2p), None,
+                                             head, ptr(logits), ptr(amax), flags, stream()))
+                return
+            check(lib.b2me_spconv_fwd_tc(ptr(x), cin, None, 0, x.shape[0], op, ptr(packed), ptr(nbr), ptr(perm),
+                                         ptr(masks), K, V, cout, None, None, None, 1, 0.0, ptr(out), op, flags,
+                                         stream()))
         run()
         torch.cuda.synchronize()
         if prof_read:

@@ -310,6 +310,22 @@ int b2me_ingest_clouds(const float* xyzrgb, int64_t n, const int32_t* frame_offs
                        float* out_xyz, float* out_rgb, float* out_bidx, int32_t* out_src, int32_t* out_offsets,
                        void* ws, size_t ws_bytes, b2me_stream_t stream);
 
+/* Order-preserving selection of the rows with key[i] == want (want < 0: key[i] != 0), e.g. the EE points
+ * np.where(seg == 2) of every frame of a batch (app/inference_engine.py:422-433). key [n] u8; src_rows [n] i32 maps
+ * row i to the row id that is written (null = i); seg_offsets [S+1] i32 (device) rows of every segment.
+ * out_rows [n] i32 capacity, out_offsets [S+1] i32: selected rows before segment s (out_offsets[S] = selected). */
+size_t b2me_select_workspace_bytes(int64_t n);
+int b2me_select_rows(const uint8_t* key, int want, const int32_t* src_rows, int64_t n, const int32_t* seg_offsets,
+                     int S, int32_t* out_rows, int32_t* out_offsets, void* ws, size_t ws_bytes, b2me_stream_t stream);
+/* crop compaction: out_xyz[i] = xyz[rows[i]], out_rgb[i] = rgb[rows[i]] (may be null), out_seg[i] = segment of row i
+ * of the selection as f32 (may be null; seg_offsets [S+1] i32 offsets INTO the selection) */
+int b2me_gather_crops(const float* xyz, const float* rgb, const int32_t* rows, int64_t m, const int32_t* seg_offsets,
+                      int S, float* out_xyz, float* out_rgb, float* out_seg, b2me_stream_t stream);
+/* center_at_origin (utils/preprocess.py:8-11) per segment: out_center [S,3] = (max + min) / 2 (float32),
+ * out_centered [n,3] = points - centre of their segment (may be null) */
+int b2me_center_segments(const float* points_xyz, const int32_t* seg_offsets, int S, float* out_center,
+                         float* out_centered, b2me_stream_t stream);
+
 /* normalize_colors (utils/preprocess.py:20-37) applied per frame of a batch on the device: rgb [n,3] f32 -> out [n,3]
  * (may alias rgb): / 255 when the frame's maximum exceeds 2, per-channel min-max rescale when the frame has a negative
  * value, - 0.5 when the result lies in [0, 1]. bidx [n] f32 frame index of every point, frame_offsets [F+1] i32 (device)

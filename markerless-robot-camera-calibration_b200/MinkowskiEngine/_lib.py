@@ -58,6 +58,10 @@ SIGNATURES = {
     "b2me_kabsch_batched": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2me_ingest_workspace_bytes": (_sz, [_i64]),
     "b2me_ingest_clouds": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b2me_select_workspace_bytes": (_sz, [_i64]),
+    "b2me_select_rows": (_i32, [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "b2me_gather_crops": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "b2me_center_segments": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "b2me_normalize_colors": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
     "b2me_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b2me_ball_query": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),

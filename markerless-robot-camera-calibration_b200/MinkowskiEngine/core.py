@@ -7,6 +7,7 @@ modules (model/backbone/minkunet.py:126-181). Each of those returns a SparseTens
 residual and activation in its epilogue) when the features are first needed. ME.cat of two tensors is a
 lazy two-source view that the convolution kernel consumes without materialising the concatenation.
 """
+import threading
 from dataclasses import dataclass, field as dc_field
 from enum import Enum
 from typing import List, Optional
@@ -54,7 +55,10 @@ class _State:
     tc_flags = 0  # B2ME_TC_FLAG_* passed to every tcgen05 launch (operand path, accumulator layout)
     fuse_head = True  # MinkowskiLinear(.., hidden) -> act -> MinkowskiLinear(hidden, C <= 16) as ONE launch
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
-    profile = None  # bench.py hook, see ops._profile_conv
+    lock = threading.Lock()  # several host threads may drive the library (one stream each, pipeline.predict_stream)
+
+
+_tls = threading.local()  # per-thread profile hook (bench.py), see ops._profile_conv
 
 
 def set_compute_dtype(dtype):
@@ -171,13 +175,19 @@ def tile_masks(nbr, perm, V, K):
 
 
 def set_profile(mode):
-    """None | 'census' | 'events' -> the record list that ops._profile_conv appends to."""
-    _State.profile = None if mode is None else dict(mode=mode, records=[])
-    return None if mode is None else _State.profile["records"]
+    """None | 'census' | 'events' -> the record list that ops._profile_conv appends to (state of the CALLING thread:
+    every host thread of a pipelined run collects the launches of its own batches)."""
+    _tls.profile = None if mode is None else dict(mode=mode, records=[])
+    return None if mode is None else _tls.profile["records"]
+
+
+def get_profile():
+    return getattr(_tls, "profile", None)
 
 
 def _count(n=1):
-    _State.launches += n
+    with _State.lock:
+        _State.launches += n
 
 
 # ------------------------------------------------------------------------------------------------ coordinate maps

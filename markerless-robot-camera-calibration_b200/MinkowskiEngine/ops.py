@@ -3,7 +3,7 @@ import torch
 
 from . import _lib
 from ._lib import lib, check, ptr, stream, dtype_code
-from .core import SparseTensor, _Pending, _State, _as_dtype, _count, CoordinateMapKey
+from .core import SparseTensor, _Pending, _State, _as_dtype, _count, CoordinateMapKey, get_profile
 
 
 # ------------------------------------------------------------------------------------------------ caches
@@ -113,7 +113,7 @@ def _profile_conv(kind, p, Cin, masks=None, extra=None):
     """bench.py hook: 'census' records the algorithmic work of every convolution launch (pairs = sum_k P_k) and, for
     the tcgen05 kernel, the (256-row tile pair, offset) passes it executes (zero-filled rows included),
     'events' brackets the launch with CUDA events on the launching stream."""
-    prof = _State.profile
+    prof = get_profile()
     if prof is None:
         return None
     if prof["mode"] == "census":

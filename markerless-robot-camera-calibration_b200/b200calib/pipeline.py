@@ -48,9 +48,10 @@ class PipelineConfig:
     kp_center_at_origin: bool = True
     translation_x_offset: float = -0.015
     num_dense_points: int = 2048   # INFERENCE.num_of_dense_input_points (PointNet++ key-point branch)
-    # is_confident = check_sanity(...) as in app/inference_engine.py:323 (host NumPy on the EE crop, b200calib/sanity.py;
-    # predict_batch only: it needs the host copy of the points). Off: is_confident = "a pose was produced".
-    sanity_check: bool = False
+    # is_confident = check_sanity(...) exactly as the reference sets it (app/inference_engine.py:323), evaluated on the
+    # device for every posed frame (b2me_sanity_check). Off: no frame is ever marked confident, so the calibration tail
+    # (calibration.calibrate_individual filters on is_confident) cannot silently average unchecked frames.
+    sanity_check: bool = True
     sanity_min_ee_points: int = 2048      # INFERENCE.SANITY.min_num_of_ee_points
     sanity_kp_error_margin: float = 0.05  # INFERENCE.KEY_POINTS.error_margin
 
@@ -68,12 +69,17 @@ class FrameResult:
     icp_stats: Optional[np.ndarray] = None
 
 
-def normalize_colors_(rgb):
-    """utils/preprocess.py:20-37 on a device tensor (the min-max branch for negative inputs is not taken by
-    valid colours)."""
-    if rgb.numel() and float(rgb.max()) > 2:
-        rgb = rgb / 255.0
-    return rgb - 0.5
+def normalize_colors_(rgb, bidx=None, offs=None):
+    """utils/preprocess.py:20-37 per frame on the device (b2me_normalize_colors: / 255, min-max branch for negative
+    inputs, - 0.5; every decision from the frame's own extrema, no host round trip). Without bidx / offs the tensor is
+    one frame."""
+    n = rgb.shape[0]
+    if n == 0:
+        return rgb
+    if bidx is None:
+        bidx = torch.zeros((n,), dtype=torch.float32, device=rgb.device)
+        offs = np.array([0, n], dtype=np.int32)
+    return out_utils.normalize_colors_batched(rgb, bidx, offs)
 
 
 def batch_frames(frames, device, pinned=None):
@@ -138,15 +144,6 @@ def _eye(C, device):
     return _EYES[k]
 
 
-def _segment_minmax(points, seg_ids, S):
-    mn = torch.full((S, 3), float("inf"), device=points.device)
-    mx = torch.full((S, 3), float("-inf"), device=points.device)
-    idx = seg_ids.unsqueeze(1).expand(-1, 3)
-    mn.scatter_reduce_(0, idx, points, reduce="amin")
-    mx.scatter_reduce_(0, idx, points, reduce="amax")
-    return mn, mx
-
-
 class _Stage:
     """opt-in per-stage wall times (device-synchronised on both sides); used by bench.py --stages only."""
 
@@ -179,34 +176,57 @@ class BatchedInferenceEngine:
 
     @torch.no_grad()
     def segment(self, points, rgb, bidx, offs):
-        """labels after the EE largest-cluster filter (app/inference_engine.py:419-433), per-frame EE counts."""
+        """labels after the EE largest-cluster filter (app/inference_engine.py:419-433), kept EE rows, per-frame
+        offsets of those rows (host)."""
         nb = len(offs) - 1
-        labels, _, _ = segment_points(self.seg_model, points, normalize_colors_(rgb), bidx, nb, self.cfg.seg_scale)
-        return self.filter_ee(points, labels, bidx, nb)
+        offs_dev = torch.as_tensor(np.asarray(offs), dtype=torch.int32).to(points.device)
+        labels, _, _ = segment_points(self.seg_model, points, normalize_colors_(rgb, bidx, offs_dev), bidx, nb,
+                                      self.cfg.seg_scale)
+        return self.filter_ee(points, labels, offs_dev, nb)
 
-    def filter_ee(self, points, labels, bidx, nb):
-        ee_idx = torch.nonzero(labels == 2).flatten()
-        labels = torch.where(labels == 2, torch.ones_like(labels), labels)
-        if ee_idx.numel() == 0:
-            return labels, ee_idx, torch.zeros(nb + 1, dtype=torch.int64)
-        ee_frame = bidx[ee_idx].long()
-        counts = torch.bincount(ee_frame, minlength=nb)
-        ee_offs = torch.zeros(nb + 1, dtype=torch.int64, device=points.device)
-        ee_offs[1:] = torch.cumsum(counts, 0)
-        ee_offs_h = ee_offs.cpu()
-        ee_pts = points[ee_idx].contiguous()
-        mask, _ = out_utils.largest_cluster_mask(ee_pts, ee_offs_h.to(torch.int32).numpy(), self.cfg.cluster_dist)
-        keep = ee_idx[mask.bool()]
-        labels[keep] = 2
-        kcounts = torch.bincount(bidx[keep].long(), minlength=nb)
-        koffs = torch.zeros(nb + 1, dtype=torch.int64)
-        koffs[1:] = torch.cumsum(kcounts, 0).cpu()
-        return labels, keep, koffs
+    def filter_ee(self, points, labels, offs_dev, nb):
+        """app/inference_engine.py:422-433 for a batch: every class-2 point becomes class 1, the largest single-linkage
+        cluster (K7) of each frame's class-2 points becomes class 2 again. Two order-preserving selections
+        (b2me_select_rows) + K7, two host syncs (EE counts, kept counts). Returns (labels [N] u8, kept rows [m] i32
+        frame-sorted, per-frame offsets of the kept rows [nb+1] host int64)."""
+        dev = points.device
+        N = labels.shape[0]
+        zero_offs = torch.zeros(nb + 1, dtype=torch.int64)
+        if N == 0:
+            return labels, torch.zeros((0,), dtype=torch.int32, device=dev), zero_offs
+        ws = torch.empty((lib.b2me_select_workspace_bytes(N),), dtype=torch.uint8, device=dev)
+        ee_rows = torch.empty((N,), dtype=torch.int32, device=dev)
+        ee_offs_d = torch.empty((nb + 1,), dtype=torch.int32, device=dev)
+        check(lib.b2me_select_rows(ptr(labels), 2, None, N, ptr(offs_dev), nb, ptr(ee_rows), ptr(ee_offs_d), ptr(ws),
+                                   ws.numel(), stream()), "select_rows")
+        _count(5)
+        labels2 = torch.where(labels == 2, torch.ones_like(labels), labels)
+        ee_offs_h = ee_offs_d.cpu().numpy()                        # host sync 1: EE points per frame
+        n_ee = int(ee_offs_h[-1])
+        if n_ee == 0:
+            return labels2, ee_rows[:0], zero_offs
+        ee_pts = torch.empty((n_ee, 3), dtype=torch.float32, device=dev)
+        check(lib.b2me_gather_crops(ptr(points), None, ptr(ee_rows), n_ee, None, 0, ptr(ee_pts), None, None, stream()),
+              "gather_crops")
+        _count(1)
+        mask, sizes = out_utils.largest_cluster_mask(ee_pts, ee_offs_h.astype(np.int32), self.cfg.cluster_dist)
+        keep = torch.empty((n_ee,), dtype=torch.int32, device=dev)
+        koffs_d = torch.empty((nb + 1,), dtype=torch.int32, device=dev)
+        check(lib.b2me_select_rows(ptr(mask), -1, ptr(ee_rows), n_ee, ptr(ee_offs_d), nb, ptr(keep), ptr(koffs_d),
+                                   ptr(ws), ws.numel(), stream()), "select_rows")
+        _count(5)
+        host = torch.cat((koffs_d, sizes)).cpu().numpy()           # host sync 2: kept points per frame + K7 status
+        if int(host[nb + 1:].min()) < 0:
+            raise RuntimeError("largest-cluster filter: a non-finite or far out-of-range EE point (b2me_largest_cluster)")
+        koffs = torch.from_numpy(host[:nb + 1].astype(np.int64))
+        keep = keep[:int(koffs[-1])]
+        labels2[keep.long()] = 2
+        return labels2, keep, koffs
 
     @torch.no_grad()
     def pose_from_ee(self, points, rgb_norm, ee_idx, ee_offs, ee2base_poses=None, kp_conf_threshold=None):
-        """rotation + translation + key points + Kabsch + ICP for the frames whose EE crop passes the gate.
-        ee_idx: rows of the EE points (frame-sorted), ee_offs [nb+1] host int64."""
+        """rotation + translation + key points + Kabsch + sanity check + ICP for the frames whose EE crop passes the
+        gate. ee_idx: rows of the EE points (frame-sorted, i32), ee_offs [nb+1] host int64."""
         cfg = self.cfg
         nb = len(ee_offs) - 1
         dev = points.device
@@ -215,22 +235,31 @@ class BatchedInferenceEngine:
         res = dict(ok_frames=ok, ee_pose=None, kp_pose=None, icp_stats=None, key_points=None)
         if len(ok) == 0 or self.rot_model is None:
             return res
-        # compact the crops of the frames that pass the gate
-        sel = torch.cat([ee_idx[int(ee_offs[f]):int(ee_offs[f + 1])] for f in ok])
+        # compact the crops of the frames that pass the gate (all of them, usually: no copy of the row list then)
         S = len(ok)
-        seg_counts = counts[ok]
+        if S == nb:
+            sel = ee_idx
+        else:
+            sel = torch.cat([ee_idx[int(ee_offs[f]):int(ee_offs[f + 1])] for f in ok])
         soffs = np.zeros(S + 1, dtype=np.int32)
-        np.cumsum(seg_counts, out=soffs[1:])
-        seg_ids = torch.repeat_interleave(torch.arange(S, device=dev), torch.as_tensor(seg_counts, device=dev))
-        pts = points[sel].contiguous()
-        feats = rgb_norm[sel].contiguous()
-        segf = seg_ids.float()
+        np.cumsum(counts[ok], out=soffs[1:])
+        soffs_dev = torch.from_numpy(soffs).to(dev)
+        m = int(soffs[-1])
+        pts = torch.empty((m, 3), dtype=torch.float32, device=dev)
+        feats = torch.empty((m, 3), dtype=torch.float32, device=dev)
+        segf = torch.empty((m,), dtype=torch.float32, device=dev)
+        check(lib.b2me_gather_crops(ptr(points), ptr(rgb_norm), ptr(sel.contiguous()), m, ptr(soffs_dev), S, ptr(pts),
+                                    ptr(feats), ptr(segf), stream()), "gather_crops")
+        # center_at_origin of every crop (utils/preprocess.py:8-11), shared by the rotation and key-point networks
+        center = torch.empty((S, 3), dtype=torch.float32, device=dev)
+        centered = torch.empty((m, 3), dtype=torch.float32, device=dev)
+        check(lib.b2me_center_segments(ptr(pts), ptr(soffs_dev), S, ptr(center), ptr(centered), stream()),
+              "center_segments")
+        _count(2)
 
         # --- rotation (app/inference_engine.py:437-457)
         with _Stage(self, "rotation"):
-            mn, mx = _segment_minmax(pts, seg_ids, S)
-            center = (mx + mn) / 2
-            rot_pts = pts - center[seg_ids] if cfg.rot_center_at_origin else pts
+            rot_pts = centered if cfg.rot_center_at_origin else pts
             fld = _field(rot_pts, feats, segf, cfg.rot_scale, S)
             rot_out = self.rot_model(fld.sparse())          # [S, 7|10]
             quat = rot_out[:, 3:7].float().contiguous()     # W,X,Y,Z
@@ -241,36 +270,49 @@ class BatchedInferenceEngine:
 
         # --- key points (app/inference_engine.py:491-559) + Kabsch (:384-393)
         kp_T = None
+        bp = kp_xyz = None
+        th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
         if self.kp_model is not None:
             with _Stage(self, "key_points"):
-                kp_pts = pts - center[seg_ids] if cfg.kp_center_at_origin else pts
+                kp_pts = centered if cfg.kp_center_at_origin else pts
                 if getattr(self.kp_model, "is_dense_pointnet2", False) or type(self.kp_model).__name__ == "PointNet2SSG":
                     # the reference's default branch (:511-537): PointNet++ on num_of_dense_input_points points drawn
                     # uniformly without replacement from every EE crop, here for all crops in one batch
-                    bp, bi = self._key_points_pointnet2(kp_pts, feats, seg_ids, soffs, S)
+                    bp, bi = self._key_points_pointnet2(kp_pts, feats, segf.long(), soffs, S)
                 else:
                     # MinkUNet branch (:539-555)
                     kfld = _field(kp_pts, feats, segf, cfg.kp_scale, S)
                     kout = self.kp_model(kfld.sparse()).slice(kfld).F.float()
                     bp, bi = out_utils.key_point_predictions_batched(kout, soffs)
-                th = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
                 K = bp.shape[1]
                 valid = bp > th                                     # [S,K]
                 nvalid = valid.sum(1)
                 # pack the selected (reference kp, predicted point) pairs to the front of each row
                 order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
                 ref = self.ref_kp.to(dev)[: K][order]               # [S,K,3]
-                tgt = pts[bi.long().clamp(min=0)].double()          # [S,K,3]
-                tgt = torch.gather(tgt, 1, order.unsqueeze(-1).expand(-1, -1, 3))
+                kp_xyz = pts[bi.long().clamp(min=0)]                # [S,K,3] f32: the EE point under every key point
+                tgt = torch.gather(kp_xyz.double(), 1, order.unsqueeze(-1).expand(-1, -1, 3))
                 R, t = rigid_transform_3D_batched(ref.contiguous(), tgt.contiguous(), nvalid.to(torch.int32))
                 kp_T = torch.zeros((S, 4, 4), dtype=torch.float64, device=dev)
                 kp_T[:, :3, :3], kp_T[:, :3, 3], kp_T[:, 3, 3] = R, t, 1.0
                 res["key_points"] = (bp, bi - torch.as_tensor(soffs[:-1], device=dev).unsqueeze(1), nvalid)
                 kp_ok = nvalid >= 4
 
+        # --- is_confident = check_sanity(data, result) (app/inference_engine.py:323, :246-279): the EE pose BEFORE the
+        #     ICP refinement against the corners / gripper tips found on the crop, and the selected key points
+        confident = None
+        if cfg.sanity_check:
+            with _Stage(self, "sanity"):
+                K6 = min(bp.shape[1], 6) if bp is not None else 0
+                confident = out_utils.sanity_check_batched(
+                    pts, soffs, ee_pose, bp[:, :K6].contiguous() if K6 else None,
+                    kp_xyz[:, :K6].contiguous() if K6 else None, th, cfg.sanity_min_ee_points,
+                    cfg.sanity_kp_error_margin)
+
         # --- ICP refinement of both poses (app/inference_engine.py:358-362): ONE launch, 2S problems
         with _Stage(self, "icp"):
             ee_T = _poses_to_matrices(ee_pose)
+            kp_T0 = kp_T          # the key-point pose before its ICP refinement (evaluation: "kp" vs "kp_icp")
             stats = kstats = None
             if cfg.icp_enabled and self.cad is not None:
                 if kp_T is not None:
@@ -283,7 +325,9 @@ class BatchedInferenceEngine:
                     ee_T, stats = icp_p2p_batched(self.cad, pts, soffs, ee_T)
         # --- one device->host transfer of everything the host needs
         with _Stage(self, "readback"):
-            pack = [ee_T.reshape(S, 16), ee_pose]   # ee_pose: before the ICP refinement (what check_sanity looks at)
+            conf_col = (confident.double() if confident is not None
+                        else torch.zeros((S,), dtype=torch.float64, device=dev)).unsqueeze(1)
+            pack = [ee_T.reshape(S, 16), ee_pose, conf_col]   # ee_pose: before the ICP refinement
             if stats is not None:
                 pack.append(stats)
             if kp_T is not None:
@@ -291,11 +335,13 @@ class BatchedInferenceEngine:
                          res["key_points"][1].double(), res["key_points"][2].double().unsqueeze(1)]
                 if kstats is not None:
                     pack.append(kstats)
+                pack.append(kp_T0.reshape(S, 16))
             host = torch.cat(pack, dim=1).cpu().numpy()
-            c = 23
+            c = 24
             res["ee_T"] = host[:, :16].reshape(S, 4, 4)
             res["ee_pose_initial"] = host[:, 16:23]
-            res["kp_threshold"] = cfg.kp_conf_threshold if kp_conf_threshold is None else kp_conf_threshold
+            res["confident"] = host[:, 23] > 0.5
+            res["kp_threshold"] = th
             if stats is not None:
                 res["icp_stats"] = host[:, c:c + 4]
                 c += 4
@@ -310,7 +356,9 @@ class BatchedInferenceEngine:
                 c += 2 * K + 1
                 if kstats is not None:
                     res["kp_icp_stats"] = host[:, c:c + 4]
+                    c += 4
                 res["kp_pose"] = get_poses_from_matrices(res["kp_T"])
+                res["kp_pose_initial"] = get_poses_from_matrices(host[:, c:c + 16].reshape(S, 4, 4))
         return res
 
     def _key_points_pointnet2(self, kp_pts, feats, seg_ids, soffs, S):
@@ -350,14 +398,15 @@ class BatchedInferenceEngine:
         [N] uint8 device tensor used for the EE crop instead of the predicted labels (random-init weights give no
         usable EE). Returns (per-point labels uint8 on the device, pose dict on the host)."""
         nb = len(offs) - 1
+        offs_dev = torch.as_tensor(np.asarray(offs), dtype=torch.int32).to(points.device)
         with _Stage(self, "segmentation"):
-            rgbn = rgb if rgb_normalized else normalize_colors_(rgb)   # b200calib.ingest already normalises
+            rgbn = rgb if rgb_normalized else normalize_colors_(rgb, bidx, offs_dev)   # b200calib.ingest normalises
             labels, fld, out = segment_points(self.seg_model, points, rgbn, bidx, nb, self.cfg.seg_scale)
             del fld, out
         seg_labels = labels
         crop_src = labels if gt_labels is None else gt_labels
         with _Stage(self, "ee_cluster"):
-            labels2, ee_idx, ee_offs = self.filter_ee(points, crop_src.clone(), bidx, nb)
+            labels2, ee_idx, ee_offs = self.filter_ee(points, crop_src, offs_dev, nb)
         if gt_labels is None:
             seg_labels = labels2
         pose = self.pose_from_ee(points, rgbn, ee_idx, ee_offs, ee2base_poses, kp_conf_threshold)
@@ -376,36 +425,113 @@ class BatchedInferenceEngine:
             gl = torch.as_tensor(np.concatenate(gt_labels).astype(np.uint8)).to(dev)
         seg_labels, pose = self.predict_device(points, rgb, bidx, offs, ee2base_poses, gl, kp_conf_threshold)
         results = self.assemble(seg_labels.cpu().numpy(), offs, pose, ee2base_poses)
-        if self.cfg.sanity_check:
-            self.apply_sanity(results, frames, offs, pose)
+        self.attach_key_points(results, frames, offs, pose)
         return results
 
-    def apply_sanity(self, results, frames, offs, pose):
-        """is_confident as the reference sets it (app/inference_engine.py:323): check_sanity on the frame's points, the
-        labels the EE crop came from, the EE pose BEFORE the ICP refinement and the selected key points."""
-        from .sanity import check_sanity
+    def predict_stream(self, batches, depth=2, fn=None, worker_init=None, **kw):
+        """Throughput mode: iterate over batches (each a tuple (points, rgb, bidx, offs) of device tensors + host
+        offsets, as predict_device takes them; or whatever `fn(item)` takes: fn runs in the worker, on its stream,
+        instead of predict_device) with `depth` batches in flight, each on its own CUDA stream and host thread
+        (`worker_init(w)` is called once in every worker thread). The small networks of batch i (rotation / key points on the EE crops: launch-bound, the host cannot
+        keep the GPU busy) then run in the gaps of the large convolutions of batch i + 1 and vice versa, and every
+        host sync of one batch is hidden behind the other's kernels. Yields (labels, pose) in batch order."""
+        import queue
+        import threading
+        dev = torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        q_in, q_out = [queue.Queue() for _ in range(depth)], [queue.Queue() for _ in range(depth)]
+
+        def worker(w):
+            torch.cuda.set_device(dev)
+            if worker_init is not None:
+                worker_init(w)
+            with torch.cuda.stream(streams[w]):
+                while True:
+                    item = q_in[w].get()
+                    if item is None:
+                        return
+                    try:
+                        streams[w].wait_stream(main)      # inputs produced on the caller's stream
+                        out = fn(item) if fn is not None else self.predict_device(*item, **kw)
+                        done = torch.cuda.Event()
+                        done.record(streams[w])
+                        q_out[w].put((out, done, None))
+                    except Exception as e:                # noqa: BLE001 - handed to the consumer
+                        q_out[w].put((None, None, e))
+
+        threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(depth)]
+        for t in threads:
+            t.start()
+        try:
+            pending = 0
+            it = iter(batches)
+            nxt = 0
+            head = 0
+            exhausted = False
+            while True:
+                while not exhausted and pending < depth:
+                    try:
+                        item = next(it)
+                    except StopIteration:
+                        exhausted = True
+                        break
+                    q_in[nxt % depth].put(item)
+                    nxt += 1
+                    pending += 1
+                if pending == 0:
+                    break
+                out, done, err = q_out[head % depth].get()
+                head += 1
+                pending -= 1
+                if err is not None:
+                    raise err
+                main.wait_event(done)                     # consumers on the caller's stream see the results
+                yield out
+        finally:
+            for w in range(depth):
+                q_in[w].put(None)
+            for t in threads:
+                t.join(timeout=5)
+
+    def attach_key_points(self, results, frames, offs, pose):
+        """ResultDTO.key_points (app/inference_engine.py:327-345): (class, xyz) of every key point above the confidence
+        threshold, from the host copy of the frames (predict_batch only)."""
+        if pose.get("key_points") is None:
+            return
         crop = pose["crop_labels"].cpu().numpy()
+        probs, idx, _ = pose["key_points"]
         for j, f in enumerate(pose["ok_frames"]):
             r = results[f]
             if r.ee_pose is None:
                 continue
-            pts_f = np.asarray(frames[f][0])
+            ee_pts = np.asarray(frames[f][0])[crop[offs[f]:offs[f + 1]] == 2]
+            r.key_points = [(int(k), ee_pts[idx[j, k]]) for k in np.nonzero(probs[j] > pose["kp_threshold"])[0]]
+
+    def host_sanity(self, results, frames, offs, pose):
+        """cross-check of the device verdict: check_sanity of the host mirror (b200calib/sanity.py, pinned by the
+        reference's own outputs) on the host copy of the frames -> list of (frame, verdict)."""
+        from .sanity import check_sanity
+        crop = pose["crop_labels"].cpu().numpy()
+        out = []
+        for j, f in enumerate(pose["ok_frames"]):
+            r = results[f]
+            if r.ee_pose is None:
+                continue
             lab_f = crop[offs[f]:offs[f + 1]]
-            kps = []
-            if pose.get("key_points") is not None:
-                probs, idx, _ = pose["key_points"]
-                ee_pts = pts_f[lab_f == 2]
-                for k in np.nonzero(probs[j] > pose["kp_threshold"])[0]:
-                    kps.append((int(k), ee_pts[idx[j, k]]))
-            r.key_points = kps
-            r.is_confident = bool(check_sanity(pts_f, lab_f, pose["ee_pose_initial"][j], kps,
-                                               self.cfg.sanity_min_ee_points, self.cfg.sanity_kp_error_margin))
+            out.append((int(f), bool(check_sanity(np.asarray(frames[f][0]), lab_f, pose["ee_pose_initial"][j],
+                                                   r.key_points, self.cfg.sanity_min_ee_points,
+                                                   self.cfg.sanity_kp_error_margin))))
+        return out
 
     @staticmethod
     def assemble(seg_h, offs, pose, ee2base_poses=None):
-        """host-side ResultDTO assembly (app/inference_engine.py:288-369)."""
+        """host-side ResultDTO assembly (app/inference_engine.py:288-369). is_confident is the device verdict of
+        check_sanity (False for every frame when PipelineConfig.sanity_check is off: unchecked frames never reach the
+        calibration average)."""
         nb = len(offs) - 1
         results = [FrameResult(segmentation=seg_h[offs[i]:offs[i + 1]]) for i in range(nb)]
+        conf = pose.get("confident")
         for j, f in enumerate(pose["ok_frames"]):
             r = results[f]
             if pose.get("ee_pose") is not None:
@@ -419,7 +545,7 @@ class BatchedInferenceEngine:
                     r.base_pose = get_base2cam_pose(r.ee_pose, ee2base_poses[f])
                 if r.key_points_pose is not None:
                     r.key_points_base_pose = get_base2cam_pose(r.key_points_pose, ee2base_poses[f])
-            r.is_confident = r.ee_pose is not None
+            r.is_confident = bool(conf[j]) if (conf is not None and r.ee_pose is not None) else False
         return results
 
 

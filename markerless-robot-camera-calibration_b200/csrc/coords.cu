@@ -926,3 +926,140 @@ extern "C" int b2me_normalize_colors(const float* rgb, const float* bidx, int64_
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }
+
+// ------------------------------------------------------------------------------------------ row selection
+// Rows of a batch that carry a given label (or a non-zero mask), frame by frame, order preserving: what the reference
+// does per frame with np.where(seg == 2) (app/inference_engine.py:422-433). flags -> exclusive scan -> scatter; the
+// per-segment offsets of the selection come out of the same scan (out_offsets[s] = rows selected before segment s).
+__global__ void k_select_flags(const uint8_t* __restrict__ key, int want, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (want < 0 ? key[i] != 0 : key[i] == (uint8_t)want) ? 1 : 0;
+}
+
+__global__ void k_select_scatter(const int32_t* __restrict__ pos, const int32_t* __restrict__ total,
+                                 const int32_t* __restrict__ src_rows, int64_t n,
+                                 const int32_t* __restrict__ seg_offsets, int S, int32_t* __restrict__ out_rows,
+                                 int32_t* __restrict__ out_offsets) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= S) {
+        const int32_t so = seg_offsets[i];
+        out_offsets[i] = so < n ? pos[so] : *total;
+    }
+    if (i >= n) return;
+    const int32_t p = pos[i];
+    const int32_t nxt = (i + 1 < n) ? pos[i + 1] : *total;
+    if (nxt != p) out_rows[p] = src_rows ? src_rows[i] : (int32_t)i;
+}
+
+extern "C" size_t b2me_select_workspace_bytes(int64_t n) {
+    const int64_t n1 = n > 0 ? n : 1;
+    return align_up((size_t)(n1 + 1) * 4, 256) + align_up(16, 256) + scan_ws_bytes(n1 + 1);
+}
+
+extern "C" int b2me_select_rows(const uint8_t* key, int want, const int32_t* src_rows, int64_t n,
+                                const int32_t* seg_offsets, int S, int32_t* out_rows, int32_t* out_offsets, void* ws,
+                                size_t ws_bytes, b2me_stream_t stream) {
+    if (!key || !seg_offsets || !out_rows || !out_offsets || !ws || n < 0 || S < 1 || want > 255) return B2ME_EINVAL;
+    if (n >= (int64_t)1 << 31) return B2ME_EINVAL;
+    if (ws_bytes < b2me_select_workspace_bytes(n)) return B2ME_EWORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    char* base = reinterpret_cast<char*>(ws);
+    int32_t* pos = reinterpret_cast<int32_t*>(base);
+    int32_t* total = reinterpret_cast<int32_t*>(base + align_up((size_t)((n > 0 ? n : 1) + 1) * 4, 256));
+    void* scan = base + align_up((size_t)((n > 0 ? n : 1) + 1) * 4, 256) + align_up(16, 256);
+    if (n > 0) k_select_flags<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(key, want, n, pos);
+    cudaMemsetAsync(pos + n, 0, 4, s);
+    const int rc = exclusive_scan_i32(pos, n + 1, total, scan, s);
+    if (rc != B2ME_OK) return rc;
+    const unsigned G = (unsigned)ceil_div64((n > S ? n : S) + 1, 256);
+    k_select_scatter<<<G, 256, 0, s>>>(pos, total, src_rows, n, seg_offsets, S, out_rows, out_offsets);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// gather of xyz / rgb rows + the frame index of every selected row (crop compaction of the EE points)
+__global__ void k_gather_crops(const float* __restrict__ xyz, const float* __restrict__ rgb,
+                               const int32_t* __restrict__ rows, int64_t m, const int32_t* __restrict__ seg_offsets,
+                               int S, float* __restrict__ out_xyz, float* __restrict__ out_rgb,
+                               float* __restrict__ out_seg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t r = rows[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        out_xyz[i * 3 + c] = xyz[r * 3 + c];
+        if (out_rgb) out_rgb[i * 3 + c] = rgb[r * 3 + c];
+    }
+    if (out_seg) {
+        int lo = 0, hi = S;  // largest s with seg_offsets[s] <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_offsets[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        out_seg[i] = (float)lo;
+    }
+}
+
+extern "C" int b2me_gather_crops(const float* xyz, const float* rgb, const int32_t* rows, int64_t m,
+                                 const int32_t* seg_offsets, int S, float* out_xyz, float* out_rgb, float* out_seg,
+                                 b2me_stream_t stream) {
+    if (!xyz || !rows || !out_xyz || m < 0 || (out_rgb && !rgb) || (out_seg && (!seg_offsets || S < 1)))
+        return B2ME_EINVAL;
+    if (m == 0) return B2ME_OK;
+    k_gather_crops<<<(unsigned)ceil_div64(m, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        xyz, rgb, rows, m, seg_offsets, S, out_xyz, out_rgb, out_seg);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// center_at_origin (utils/preprocess.py:8-11) per segment: offset = (max + min) / 2 in float32, points - offset
+__global__ void __launch_bounds__(256) k_center_segments(const float* __restrict__ pts,
+                                                         const int32_t* __restrict__ seg_offsets,
+                                                         float* __restrict__ out_center,
+                                                         float* __restrict__ out_centered) {
+    __shared__ float smin[3][8], smax[3][8];
+    __shared__ float off_s[3];
+    const int seg = blockIdx.x;
+    const int r0 = seg_offsets[seg], r1 = seg_offsets[seg + 1];
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = pts[(int64_t)r * 3 + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { smin[c][threadIdx.x >> 5] = mn[c]; smax[c][threadIdx.x >> 5] = mx[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = smin[threadIdx.x][0], b = smax[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) { a = fminf(a, smin[threadIdx.x][w]); b = fmaxf(b, smax[threadIdx.x][w]); }
+        const float o = r1 > r0 ? __fmul_rn(__fadd_rn(b, a), 0.5f) : 0.f;
+        off_s[threadIdx.x] = o;
+        out_center[seg * 3 + threadIdx.x] = o;
+    }
+    __syncthreads();
+    if (!out_centered) return;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out_centered[(int64_t)r * 3 + c] = __fsub_rn(pts[(int64_t)r * 3 + c], off_s[c]);
+}
+
+extern "C" int b2me_center_segments(const float* points_xyz, const int32_t* seg_offsets, int S, float* out_center,
+                                    float* out_centered, b2me_stream_t stream) {
+    if (!points_xyz || !seg_offsets || !out_center || S < 0) return B2ME_EINVAL;
+    if (S == 0) return B2ME_OK;
+    k_center_segments<<<(unsigned)S, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(points_xyz, seg_offsets,
+                                                                                         out_center, out_centered);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}

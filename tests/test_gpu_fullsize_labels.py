@@ -28,7 +28,8 @@ def fullsize():
     cseg = bench.build_models(ME)[0].cuda()
     torch.set_num_threads(max(1, torch.get_num_threads()))
     ref = []
-    for p, c, _ in frames:                                        # the reference runs one frame at a time
+    for fr in frames:                                             # the reference runs one frame at a time
+        p, c = fr[0], fr[1]
         with torch.no_grad():
             _, raw = OP.predict_segmentation(oseg, p, OP.normalize_colors(c), 200.0)
         ref.append(raw)

@@ -114,6 +114,28 @@ int b2me_stride_kernel_maps(const int32_t* in2out, const uint8_t* koff, int64_t 
 int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, const void* table, size_t table_bytes,
                        int32_t* nbr, uint32_t* tile_mask, b2me_stream_t stream);
 
+/* K3 for large maps through 4 x 4 x 4 blocks: the coordinate map at tensor stride 4 ts (two stride-2 levels above
+ * this one) lists the occupied blocks and its table maps a block origin to its row.
+ *   b2me_block_rows: brows [V_blocks,64] i32 = voxel row in every cell of every block (-1 = empty), from the two parent
+ *                    maps in2out1 [V] (ts -> 2 ts) and in2out2 [V_2ts] (2 ts -> 4 ts) of b2me_stride_map
+ *   b2me_kernel_map_k3_blocks: same nbr [V,27] as b2me_kernel_map_k3 (1..8 probes of the small block table per voxel
+ *                    instead of 26 of the voxel table; results staged in shared memory, contiguous stores), plus
+ *                    row_masks [V] u32 (bit k = neighbour k present) and offset_counts [32] u32 (neighbours per offset)
+ *   b2me_row_masks:  row_masks / offset_counts of an existing nbr [V,K] table (maps built by b2me_kernel_map_k3) */
+int b2me_block_rows(const int32_t* coords, int64_t V, int ts, const int32_t* in2out1, const int32_t* in2out2,
+                    int64_t V_blocks, int32_t* brows, b2me_stream_t stream);
+int b2me_kernel_map_k3_blocks(const int32_t* coords, int64_t V, int ts, const void* block_table,
+                              size_t block_table_bytes, const int32_t* brows, int32_t* nbr, uint32_t* row_masks,
+                              uint32_t* offset_counts, b2me_stream_t stream);
+int b2me_row_masks(const int32_t* nbr, int64_t V, int K, uint32_t* row_masks, uint32_t* offset_counts,
+                   b2me_stream_t stream);
+/* K3b from row masks: the keys of b2me_mask_sort_keys and the tile masks of b2me_tc_tile_masks without reading the
+ * nbr table again (4 bytes per row instead of 4 K) */
+int b2me_mask_sort_keys_rows(const uint32_t* row_masks, const uint32_t* offset_counts, int64_t V, int K, int32_t* keys,
+                             b2me_stream_t stream);
+int b2me_tile_masks_rows(const uint32_t* row_masks, const int32_t* perm, int64_t V, uint32_t* masks,
+                         b2me_stream_t stream);
+
 /*
  * K3b: sort keys for the row permutation the tcgen05 convolution takes (`perm`): key[row] = the row's K-bit
  * neighbour-occupancy mask of `nbr` [V,K], bits ordered rarest offset first. Rows sorted by key make 128-row

@@ -28,6 +28,11 @@ SIGNATURES = {
     "b2me_stride_map": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "b2me_stride_kernel_maps": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b2me_kernel_map_k3": (_i32, [_vp, _i64, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "b2me_block_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "b2me_kernel_map_k3_blocks": (_i32, [_vp, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "b2me_row_masks": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "b2me_mask_sort_keys_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "b2me_tile_masks_rows": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "b2me_mask_sort_keys": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "b2me_mask_sort_keys2_ws_bytes": (_sz, [_i64]),
     "b2me_mask_sort_keys2": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),

@@ -49,6 +49,7 @@ class _State:
     # k3 maps: Morton order inside a mask group (b2me_mask_sort_keys_morton). Off by default: measured on one box, the
     # convolution rate does not change (MMA-executed 1053-1060 vs 1058-1068 TFLOP/s) and the 64-bit sort costs ~2 ms
     mask_sort_morton = False
+    k3_block_min_rows = 65536  # k3 kernel maps of at least this many rows go through 4x4x4 blocks (b2me_kernel_map_k3_blocks)
     compute_dtype = torch.float32
     # "bf16" activations on tcgen05 | "tf32": fp32 activations holding tf32 values on tcgen05 kind::tf32 | "f32": SIMT
     compute_mode = "f32"
@@ -133,14 +134,22 @@ def set_mask_sort_two_level(on):
     _State.mask_sort_two_level = bool(on)
 
 
+def set_k3_block_min_rows(rows):
+    """k3 kernel maps with at least `rows` rows are built through the 4 x 4 x 4 block arrays of the map two stride-2
+    levels up (1..8 probes of a small table per voxel instead of 26 of the voxel table); smaller ones, and maps whose
+    coarser levels cannot be formed, use the direct probe kernel. Identical maps either way."""
+    _State.k3_block_min_rows = int(rows)
+
+
 def set_mask_sort_block(rows):
     """rows of one locality block of the mask sort (0 = sort the whole map by mask only)."""
     _State.mask_sort_block = int(rows)
 
 
-def mask_sorted_perm(nbr, V, K, block_rows=None, coords=None, ts=1):
+def mask_sorted_perm(nbr, V, K, block_rows=None, coords=None, ts=1, row_masks=None, offset_counts=None):
     """row order that groups rows with the same neighbour pattern inside blocks of `block_rows` consecutive rows
-    (K3b keys + a device sort)."""
+    (K3b keys + a device sort). With row_masks / offset_counts (by-products of the kernel-map pass) the keys come from
+    4 bytes per row instead of the whole nbr table."""
     if block_rows is None:
         block_rows = _State.mask_sort_block
     ws = torch.empty((128,), dtype=torch.uint8, device=nbr.device)
@@ -149,27 +158,37 @@ def mask_sorted_perm(nbr, V, K, block_rows=None, coords=None, ts=1):
         keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
         check(lib.b2me_mask_sort_keys_morton(ptr(nbr), ptr(coords), V, K, int(ts), ptr(keys), ptr(ws), ws.numel(),
                                              stream()), "mask_sort_keys_morton")
+        _count(2)
     elif block_rows == 0 and _State.mask_sort_two_level and K == 27:
         # two-level keys: global rarest-first segment + per-segment order of the remaining offsets
         ws = torch.empty((lib.b2me_mask_sort_keys2_ws_bytes(V),), dtype=torch.uint8, device=nbr.device)
         keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
         check(lib.b2me_mask_sort_keys2(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys2")
-        _count(2)
+        _count(4)
+    elif block_rows == 0 and row_masks is not None:
+        keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
+        check(lib.b2me_mask_sort_keys_rows(ptr(row_masks), ptr(offset_counts), V, K, ptr(keys), stream()),
+              "mask_sort_keys_rows")
+        _count(1)
     elif block_rows == 0:  # mask-only keys fit 32 bits: half the radix passes of the device sort
         keys = torch.empty((max(V, 1),), dtype=torch.int32, device=nbr.device)
         check(lib.b2me_mask_sort_keys(ptr(nbr), V, K, ptr(keys), ptr(ws), ws.numel(), stream()), "mask_sort_keys")
+        _count(2)
     else:
         keys = torch.empty((max(V, 1),), dtype=torch.int64, device=nbr.device)
         check(lib.b2me_mask_sort_keys64(ptr(nbr), V, K, block_rows, ptr(keys), ptr(ws), ws.numel(), stream()),
               "mask_sort_keys64")
-    _count(2)
+        _count(2)
     return torch.sort(keys[:V])[1].to(torch.int32)
 
 
-def tile_masks(nbr, perm, V, K):
+def tile_masks(nbr, perm, V, K, row_masks=None):
     """per 256-row tile pair: the kernel offsets any of its rows needs (consumed by b2me_spconv_fwd_tc)."""
     masks = torch.empty(((max(V, 1) + 255) // 256,), dtype=torch.int32, device=nbr.device)
-    check(lib.b2me_tc_tile_masks(ptr(nbr), ptr(perm), V, K, ptr(masks), stream()), "tc_tile_masks")
+    if row_masks is not None:
+        check(lib.b2me_tile_masks_rows(ptr(row_masks), ptr(perm), V, ptr(masks), stream()), "tile_masks_rows")
+    else:
+        check(lib.b2me_tc_tile_masks(ptr(nbr), ptr(perm), V, K, ptr(masks), stream()), "tc_tile_masks")
     _count(1)
     return masks
 
@@ -220,6 +239,7 @@ class _Level:
         self.table = table    # uint8 device buffer (b2me_table_bytes)
         self.V = V
         self.nbr_k3 = None
+        self.masks_k3 = None  # (row occupancy masks [V] i32, per-offset neighbour counts [32] i32) of the k3 map
         self.perm_k3 = None
         self.down = None      # dict(in2out, koff, nbr_down, nbr_up, coarse_key)
         self.batch_size = None
@@ -274,14 +294,44 @@ class CoordinateManager:
         return self.levels[key].coords
 
     # -- K3
+    def _block_parents(self, key):
+        """(in2out ts -> 2 ts, in2out 2 ts -> 4 ts, level at 4 ts) when both stride-2 maps above `key` can be formed."""
+        try:
+            k1, rec1 = self.stride_down(key)
+            k2, rec2 = self.stride_down(k1)
+        except _lib.B2MEError:
+            return None
+        lv2 = self.levels[k2]
+        if lv2.table is None or lv2.V == 0:
+            return None
+        return rec1["in2out"], rec2["in2out"], lv2
+
     def kernel_map_k3(self, key):
         lv = self.levels[key]
         if lv.nbr_k3 is None:
-            nbr = torch.empty((max(lv.V, 1), 27), dtype=torch.int32, device=lv.coords.device)
-            check(lib.b2me_kernel_map_k3(ptr(lv.coords), lv.V, key._ts, ptr(lv.table), lv.table.numel(), ptr(nbr),
-                                         None, stream()), "kernel_map_k3")
-            _count(1)
+            dev = lv.coords.device
+            nbr = torch.empty((max(lv.V, 1), 27), dtype=torch.int32, device=dev)
+            row_masks = torch.empty((max(lv.V, 1),), dtype=torch.int32, device=dev)
+            counts = torch.empty((32,), dtype=torch.int32, device=dev)
+            parents = self._block_parents(key) if lv.V >= _State.k3_block_min_rows else None
+            if parents is not None:
+                # large map: through the 4 x 4 x 4 blocks = the rows of the map two stride-2 levels up (the UNet's own
+                # coordinate hierarchy; those maps are cached for the stride-2 convolutions that follow)
+                in2out1, in2out2, lv2 = parents
+                brows = torch.empty((max(lv2.V, 1) * 64,), dtype=torch.int32, device=dev)
+                check(lib.b2me_block_rows(ptr(lv.coords), lv.V, key._ts, ptr(in2out1), ptr(in2out2), lv2.V, ptr(brows),
+                                          stream()), "block_rows")
+                check(lib.b2me_kernel_map_k3_blocks(ptr(lv.coords), lv.V, key._ts, ptr(lv2.table), lv2.table.numel(),
+                                                    ptr(brows), ptr(nbr), ptr(row_masks), ptr(counts), stream()),
+                      "kernel_map_k3_blocks")
+                _count(4)
+            else:
+                check(lib.b2me_kernel_map_k3(ptr(lv.coords), lv.V, key._ts, ptr(lv.table), lv.table.numel(), ptr(nbr),
+                                             None, stream()), "kernel_map_k3")
+                check(lib.b2me_row_masks(ptr(nbr), lv.V, 27, ptr(row_masks), ptr(counts), stream()), "row_masks")
+                _count(3)
             lv.nbr_k3 = nbr[:lv.V]
+            lv.masks_k3 = (row_masks[:lv.V], counts)
         return lv.nbr_k3
 
     def perm_k3(self, key):
@@ -289,9 +339,11 @@ class CoordinateManager:
         lv = self.levels[key]
         if lv.perm_k3 is None:
             nbr = self.kernel_map_k3(key)
-            perm = (mask_sorted_perm(nbr, lv.V, 27, coords=lv.coords, ts=key._ts)
+            row_masks, counts = lv.masks_k3
+            perm = (mask_sorted_perm(nbr, lv.V, 27, coords=lv.coords, ts=key._ts, row_masks=row_masks,
+                                     offset_counts=counts)
                     if (_State.mask_sort and lv.V >= _State.mask_sort_min_rows) else None)
-            lv.perm_k3 = (perm, tile_masks(nbr, perm, lv.V, 27))
+            lv.perm_k3 = (perm, tile_masks(nbr, perm, lv.V, 27, row_masks=row_masks))
         return lv.perm_k3
 
     def perm_stride(self, rec, which):

@@ -446,6 +446,162 @@ extern "C" int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, cons
     return B2ME_OK;
 }
 
+// ---- K3 through 4 x 4 x 4 blocks (large maps). The coordinate hierarchy of the network already holds the map at
+// tensor stride 4 ts (two stride-2 levels up): its rows ARE the occupied 4 x 4 x 4 blocks of this level and its hash
+// table (a few MB: L2-resident) maps a block origin to its row. `brows[B, 64]` = the voxel of every cell of block B.
+// A voxel's 27 neighbours lie in its own block and in at most one other block per axis, so a thread probes the
+// (small) block table 1..8 times (3.4 on average) instead of the (large) voxel table 26 times, and reads its
+// neighbours out of 256-byte block arrays that the threads next to it (scan-line order) read too: cache hits instead
+// of 26 random DRAM sectors. The 256 x 27 results of a CTA are staged in shared memory and leave as one contiguous
+// 27.6 KB store; the row's occupancy mask (27 bits) and the per-offset neighbour counts of the map (inputs of the
+// K3b sort keys / tile masks) come out of the same pass.
+__global__ void k_block_rows(const int4* __restrict__ coords, int64_t V, int shift, const int32_t* __restrict__ in2out1,
+                             const int32_t* __restrict__ in2out2, int32_t* __restrict__ brows) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int4 c = __ldg(coords + v);
+    const int32_t p1 = in2out1[v];
+    if (p1 < 0) return;
+    const int32_t blk = in2out2[p1];
+    if (blk < 0) return;
+    const int l = ((c.y >> shift) & 3) | (((c.z >> shift) & 3) << 2) | (((c.w >> shift) & 3) << 4);
+    brows[(int64_t)blk * 64 + l] = (int32_t)v;
+}
+
+extern "C" int b2me_block_rows(const int32_t* coords, int64_t V, int ts, const int32_t* in2out1,
+                               const int32_t* in2out2, int64_t V_blocks, int32_t* brows, b2me_stream_t stream) {
+    if (!coords || !in2out1 || !in2out2 || !brows || V < 0 || V_blocks < 0 || ts < 1 || (ts & (ts - 1))) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (V_blocks > 0) cudaMemsetAsync(brows, 0xFF, (size_t)V_blocks * 64 * sizeof(int32_t), s);
+    if (V == 0) return B2ME_OK;
+    int shift = 0;
+    while ((1 << shift) < ts) ++shift;
+    k_block_rows<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(reinterpret_cast<const int4*>(coords), V, shift, in2out1,
+                                                             in2out2, brows);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+#define K3B_THREADS 256
+__global__ void __launch_bounds__(K3B_THREADS)
+k_kernel_map_k3_blocks(const int4* __restrict__ coords, int64_t V, int ts, int shift, const HashSlot* __restrict__ btab,
+                       unsigned long long bmask, const int32_t* __restrict__ brows, int32_t* __restrict__ nbr,
+                       uint32_t* __restrict__ row_masks, unsigned int* __restrict__ offset_counts) {
+    __shared__ int32_t res_s[K3B_THREADS * 27];   // [thread][offset]: stride 27 words, conflict-free
+    __shared__ uint32_t brow_s[8][K3B_THREADS];   // block row of the (x, y, z)-crossing combination, per thread
+    __shared__ unsigned int cnt_s[27];
+    const int tid = threadIdx.x;
+    if (tid < 27) cnt_s[tid] = 0u;
+    __syncthreads();
+    const int64_t v0 = (int64_t)blockIdx.x * K3B_THREADS;
+    const int64_t v = v0 + tid;
+    uint32_t m = 0u;
+    if (v < V) {
+        const int4 c = __ldg(coords + v);
+        const int bs = 4 * ts;
+        const int o[3] = {c.y & ~(bs - 1), c.z & ~(bs - 1), c.w & ~(bs - 1)};     // block origin (floor to 4 ts)
+        const int li[3] = {(c.y >> shift) & 3, (c.z >> shift) & 3, (c.w >> shift) & 3};
+        int dir[3];                                                                // the one other block an axis can reach
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dir[a] = li[a] == 0 ? -1 : (li[a] == 3 ? 1 : 0);
+#pragma unroll
+        for (int combo = 0; combo < 8; ++combo) {
+            const int bx = combo & 1, by = (combo >> 1) & 1, bz = combo >> 2;
+            uint32_t r = 0xFFFFFFFFu;
+            if ((!bx || dir[0]) && (!by || dir[1]) && (!bz || dir[2])) {
+                const int x = o[0] + bx * dir[0] * bs, y = o[1] + by * dir[1] * bs, z = o[2] + bz * dir[2] * bs;
+                if (coord_in_range(c.x, x, y, z)) r = table_lookup(btab, bmask, pack_key(c.x, x, y, z));
+            }
+            brow_s[combo][tid] = r;
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const int d[3] = {k % 3 - 1, (k / 3) % 3 - 1, k / 9 - 1};
+            int combo = 0, l = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int n = li[a] + d[a];
+                combo |= ((n < 0 || n > 3) ? 1 : 0) << a;
+                l |= (n & 3) << (2 * a);
+            }
+            int32_t r;
+            if (k == 13) {
+                r = (int32_t)v;
+            } else {
+                const uint32_t B = brow_s[combo][tid];
+                r = (B == 0xFFFFFFFFu) ? -1 : __ldg(brows + (int64_t)B * 64 + l);
+            }
+            res_s[tid * 27 + k] = r;
+            m |= (r >= 0 ? 1u : 0u) << k;
+        }
+        row_masks[v] = m;
+    }
+    // per-offset neighbour counts of the map: one ballot per offset and warp
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const unsigned int b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if ((tid & 31) == 0 && b) atomicAdd(&cnt_s[k], (unsigned int)__popc(b));
+    }
+    __syncthreads();
+    const int64_t nvalid = (V - v0) < K3B_THREADS ? (V - v0) : K3B_THREADS;
+    int32_t* dst = nbr + v0 * 27;
+    for (int i = tid; i < (int)nvalid * 27; i += K3B_THREADS) dst[i] = res_s[i];
+    if (tid < 27 && cnt_s[tid]) atomicAdd(offset_counts + tid, cnt_s[tid]);
+}
+
+// row masks + per-offset counts from an existing nbr table (small maps built by the direct kernel; K = 8 maps)
+__global__ void __launch_bounds__(256) k_row_masks(const int32_t* __restrict__ nbr, int64_t V, int K,
+                                                   uint32_t* __restrict__ row_masks,
+                                                   unsigned int* __restrict__ offset_counts) {
+    __shared__ unsigned int cnt_s[32];
+    if (threadIdx.x < 32) cnt_s[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0u;
+    if (v < V) {
+        for (int k = 0; k < K; ++k)
+            if (__ldg(nbr + v * K + k) >= 0) m |= 1u << k;
+        row_masks[v] = m;
+    }
+    for (int k = 0; k < K; ++k) {
+        const unsigned int b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt_s[k], (unsigned int)__popc(b));
+    }
+    __syncthreads();
+    if (threadIdx.x < K && cnt_s[threadIdx.x]) atomicAdd(offset_counts + threadIdx.x, cnt_s[threadIdx.x]);
+}
+
+extern "C" int b2me_row_masks(const int32_t* nbr, int64_t V, int K, uint32_t* row_masks, uint32_t* offset_counts,
+                              b2me_stream_t stream) {
+    if (!nbr || !row_masks || !offset_counts || V < 0 || K < 1 || K > 31) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(offset_counts, 0, 32 * sizeof(uint32_t), s);
+    if (V == 0) return B2ME_OK;
+    k_row_masks<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(nbr, V, K, row_masks, offset_counts);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+extern "C" int b2me_kernel_map_k3_blocks(const int32_t* coords, int64_t V, int ts, const void* block_table,
+                                         size_t block_table_bytes, const int32_t* brows, int32_t* nbr,
+                                         uint32_t* row_masks, uint32_t* offset_counts, b2me_stream_t stream) {
+    if (!coords || !block_table || !brows || !nbr || !row_masks || !offset_counts || V < 0 || ts < 1 || (ts & (ts - 1)))
+        return B2ME_EINVAL;
+    if (ts > (1 << 14)) return B2ME_EINVAL;
+    const int64_t slots = (int64_t)(block_table_bytes / sizeof(HashSlot));
+    if (slots < 2 || (slots & (slots - 1))) return B2ME_EINVAL;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(offset_counts, 0, 32 * sizeof(uint32_t), s);
+    if (V == 0) return B2ME_OK;
+    int shift = 0;
+    while ((1 << shift) < ts) ++shift;
+    k_kernel_map_k3_blocks<<<(unsigned)ceil_div64(V, K3B_THREADS), K3B_THREADS, 0, s>>>(
+        reinterpret_cast<const int4*>(coords), V, ts, shift, reinterpret_cast<const HashSlot*>(block_table),
+        (unsigned long long)(slots - 1), brows, nbr, row_masks, offset_counts);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
 // ------------------------------------------------------------------------------------------ K3b
 // Sort keys for the convolution's row permutation: rows with the same neighbour pattern are made adjacent so
 // that a 128-row tile of the gather-GEMM kernel needs few kernel offsets (the tile skips an offset when none of
@@ -559,6 +715,65 @@ extern "C" int b2me_mask_sort_keys(const int32_t* nbr, int64_t V, int K, int32_t
     if (blocks > B2ME_NUM_SMS * 16) blocks = B2ME_NUM_SMS * 16;
     k_offset_counts<<<(unsigned)blocks, 256, 0, s>>>(nbr, total, K, counts);
     k_mask_keys<<<(unsigned)ceil_div64(V, 256), 256, 0, s>>>(nbr, V, K, counts, keys);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// the same keys from the per-row occupancy masks + per-offset counts that the kernel-map pass already produced
+// (4 bytes per row instead of 4 K: the nbr table is not read again)
+__global__ void __launch_bounds__(256) k_mask_keys_rows(const uint32_t* __restrict__ row_masks, int64_t V, int K,
+                                                        const unsigned int* __restrict__ counts,
+                                                        int32_t* __restrict__ keys) {
+    __shared__ int bitpos[32];
+    if (threadIdx.x < K) {
+        const unsigned int mine = counts[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+            const unsigned int c = counts[j];
+            if (c < mine || (c == mine && j < (int)threadIdx.x)) ++rank;
+        }
+        bitpos[threadIdx.x] = K - 1 - rank;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const uint32_t m = __ldg(row_masks + v);
+    unsigned int key = 0u;
+    for (int k = 0; k < K; ++k)
+        if ((m >> k) & 1u) key |= 1u << bitpos[k];
+    keys[v] = (int32_t)reflect_key(key);
+}
+
+extern "C" int b2me_mask_sort_keys_rows(const uint32_t* row_masks, const uint32_t* offset_counts, int64_t V, int K,
+                                        int32_t* keys, b2me_stream_t stream) {
+    if (!row_masks || !offset_counts || !keys || V < 0 || K < 1 || K > 31) return B2ME_EINVAL;
+    if (V == 0) return B2ME_OK;
+    k_mask_keys_rows<<<(unsigned)ceil_div64(V, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        row_masks, V, K, offset_counts, keys);
+    B2ME_CHECK_LAUNCH();
+    return B2ME_OK;
+}
+
+// per 256-row tile pair of the permuted order: OR of the row masks (one thread per row, warp OR, 8 warps per pair)
+__global__ void __launch_bounds__(256) k_tile_masks_rows(const uint32_t* __restrict__ row_masks,
+                                                         const int32_t* __restrict__ perm, int64_t V,
+                                                         uint32_t* __restrict__ masks) {
+    __shared__ uint32_t part[8];
+    const int64_t slot = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t m = 0u;
+    if (slot < V) m = __ldg(row_masks + (perm ? (int64_t)__ldg(perm + slot) : slot));
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) masks[blockIdx.x] = part[0] | part[1] | part[2] | part[3] | part[4] | part[5] | part[6] | part[7];
+}
+
+extern "C" int b2me_tile_masks_rows(const uint32_t* row_masks, const int32_t* perm, int64_t V, uint32_t* masks,
+                                    b2me_stream_t stream) {
+    if (!row_masks || !masks || V < 0) return B2ME_EINVAL;
+    if (V == 0) return B2ME_OK;
+    k_tile_masks_rows<<<(unsigned)ceil_div64(V, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(row_masks, perm,
+                                                                                                       V, masks);
     B2ME_CHECK_LAUNCH();
     return B2ME_OK;
 }

@@ -305,27 +305,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// branch-free activation: x > 0 ? x : x * neg_mul + 0 with neg_mul = 1 (none), 0 (ReLU), slope (LeakyReLU). The "+ 0"
-// turns the -0 of a zeroed negative into +0 (what `x > 0 ? x : 0` gives). A runtime `switch (act)` around every element
-// compiled into two uniform branches per value in the fused-head epilogue (~1400 cycles per 32-column chunk).
-__device__ __forceinline__ float tc_act(float x, float neg_mul) { return x > 0.f ? x : fmaf(x, neg_mul, 0.f); }
+// Activation of N accumulator values with ONE uniform branch around the loop (a runtime `switch (act)` around every
+// element compiled into two uniform branches per value in the fused-head epilogue: ~1400 cycles per 32-column chunk).
+// mode 0 none, 1 ReLU (max(x, 0)), 2 LeakyReLU with slope in [0, 1] as max(x, slope x), 3 any other slope.
+__device__ __forceinline__ int tc_act_mode(int act, float slope) {
+    if (act == B2ME_ACT_RELU) return 1;
+    if (act == B2ME_ACT_LEAKY) return (slope >= 0.f && slope <= 1.f) ? 2 : 3;
+    return 0;
+}
+template <int N>
+__device__ __forceinline__ void tc_act_n(float (&v)[N], int mode, float slope) {
+    if (mode == 1) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = fmaxf(v[q], 0.f);
+    } else if (mode == 2) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = fmaxf(v[q], v[q] * slope);
+    } else if (mode == 3) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * slope;
+    }
+}
 
 // fused head: acc[c] += x[q] * W2[col0 + q][c] for the 32 columns of one accumulator chunk; W2 rows of HCP floats in
 // shared memory (every lane reads the same address: broadcast)
-template <int HCP, int NH>
-__device__ __forceinline__ void tc_head_accumulate(const float (&x)[32], const float* __restrict__ w_rows,
+template <int HC, int NH>
+__device__ __forceinline__ void tc_head_accumulate(const float (&x)[32], const float* __restrict__ w_rows, int hcp,
                                                    float (&hacc)[NH]) {
-    static_assert(HCP <= NH, "head accumulators");
+    static_assert(HC <= NH, "head accumulators");
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
+        float w[(HC + 3) / 4 * 4];
 #pragma unroll
-        for (int g = 0; g < HCP / 4; ++g) {
-            const float4 w = *reinterpret_cast<const float4*>(w_rows + q * HCP + 4 * g);
-            hacc[4 * g + 0] = fmaf(x[q], w.x, hacc[4 * g + 0]);
-            hacc[4 * g + 1] = fmaf(x[q], w.y, hacc[4 * g + 1]);
-            hacc[4 * g + 2] = fmaf(x[q], w.z, hacc[4 * g + 2]);
-            hacc[4 * g + 3] = fmaf(x[q], w.w, hacc[4 * g + 3]);
+        for (int g = 0; g < (HC + 3) / 4; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(w_rows + q * hcp + 4 * g);
+            w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
         }
+#pragma unroll
+        for (int c = 0; c < HC; ++c) hacc[c] = fmaf(x[q], w[c], hacc[c]);
     }
 }
 
@@ -753,7 +770,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         // the column half e >> 2 of the tile
         const int ew = warp - 8;
         const int we = ew & 3, chalf = ew >> 2;
-        const float neg_mul = p.act == B2ME_ACT_RELU ? 0.f : (p.act == B2ME_ACT_LEAKY ? p.slope : 1.f);
+        const int act_mode = tc_act_mode(p.act, p.slope);
         const uint32_t lane_addr0 = tmem_base + ((uint32_t)(we * 32) << 16);
         const uint32_t stg = stage_out + (uint32_t)ew * TC_STAGE_OUT_BYTES;
         // staging image: row r (0..31) = 64 bytes, 16-byte piece q stored at q ^ ((r >> 1) & 3): conflict-free for both
@@ -837,21 +854,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         const int col = n0 + cb + q4 * 4;
                         const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
                         const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
-                        x[q4 * 4 + 0] = tc_act(__uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x, neg_mul);
-                        x[q4 * 4 + 1] = tc_act(__uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y, neg_mul);
-                        x[q4 * 4 + 2] = tc_act(__uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z, neg_mul);
-                        x[q4 * 4 + 3] = tc_act(__uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w, neg_mul);
+                        x[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                        x[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                        x[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                        x[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
                     }
+                    tc_act_n(x, act_mode, p.slope);
                     // the hidden activation is a bf16 (tf32-rounded fp32) tensor in the unfused data path: same rounding
+                    if (ES == 2) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        x[q] = ES == 2 ? __bfloat162float(__float2bfloat16_rn(x[q])) : round_tf32(x[q]);
+                        for (int q = 0; q < 32; q += 2) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(x[q], x[q + 1]);
+                            const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
+                            x[q] = __uint_as_float(u << 16);
+                            x[q + 1] = __uint_as_float(u & 0xFFFF0000u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) x[q] = round_tf32(x[q]);
+                    }
                     const float* w_rows = head_w_s + (n0 + cb) * p.head_cp;
-                    switch (p.head_cp) {
-                        case 4: tc_head_accumulate<4>(x, w_rows, hacc); break;
-                        case 8: tc_head_accumulate<8>(x, w_rows, hacc); break;
-                        case 12: tc_head_accumulate<12>(x, w_rows, hacc); break;
-                        default: tc_head_accumulate<16>(x, w_rows, hacc); break;
+                    switch (p.head_c) {   // exact FMA count for the class counts of the reference's heads
+                        case 2: tc_head_accumulate<2>(x, w_rows, p.head_cp, hacc); break;
+                        case 3: tc_head_accumulate<3>(x, w_rows, p.head_cp, hacc); break;
+                        case 4: tc_head_accumulate<4>(x, w_rows, p.head_cp, hacc); break;
+                        case 6: tc_head_accumulate<6>(x, w_rows, p.head_cp, hacc); break;
+                        case 10: tc_head_accumulate<10>(x, w_rows, p.head_cp, hacc); break;
+                        default:
+                            if (p.head_cp <= 8) tc_head_accumulate<8>(x, w_rows, p.head_cp, hacc);
+                            else tc_head_accumulate<16>(x, w_rows, p.head_cp, hacc);
+                            break;
                     }
                 }
                 if (nt == NT - 1) {
@@ -969,14 +1001,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         }
                         __syncwarp();  // every lane has read its residual row before the buffer takes the outputs
                     }
+                    tc_act_n(v, act_mode, p.slope);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         uint32_t wv[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float x0 = tc_act(v[q4 * 8 + 2 * e], neg_mul);
-                            const float x1 = tc_act(v[q4 * 8 + 2 * e + 1], neg_mul);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[q4 * 8 + 2 * e], v[q4 * 8 + 2 * e + 1]);
                             wv[e] = *reinterpret_cast<uint32_t*>(&h);
                         }
                         st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
@@ -1041,10 +1072,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             }
                         }
                     }
+                    tc_act_n(v, act_mode, p.slope);
+                    if (p.out_dtype == B2ME_TF32) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        v[q] = tc_act(v[q], neg_mul);
-                        if (p.out_dtype == B2ME_TF32) v[q] = round_tf32(v[q]);
+                        for (int q = 0; q < 16; ++q) v[q] = round_tf32(v[q]);
                     }
                     float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
 #pragma unroll

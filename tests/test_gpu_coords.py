@@ -69,6 +69,53 @@ def test_sparse_tensor_int_coords_first_wins():
     assert torch.equal(c.C.cpu(), o.C) and torch.equal(c.F.cpu(), o.F)
 
 
+def test_k3_block_path_equals_direct_path_and_oracle():
+    """K3 through 4 x 4 x 4 blocks (b2me_block_rows + b2me_kernel_map_k3_blocks: the path of the large maps) against
+    the direct probe kernel and the oracle, at three tensor strides, with negative coordinates and two frames; the
+    K3b by-products (row masks, per-offset counts) give the same sort keys and tile masks as the nbr-table kernels."""
+    import MinkowskiEngine as ME
+    from MinkowskiEngine._lib import lib, ptr, stream, check
+    pts = [kinect_like_cloud(60000, 31), kinect_like_cloud(45000, 32) - np.float32(1.5)]
+    feats = [np.zeros((len(p), 1), np.float32) for p in pts]
+    maps = {}
+    for mode, thr in (("blocks", 1), ("direct", 1 << 40)):
+        ME.set_k3_block_min_rows(thr)
+        try:
+            of, cf = _fields(pts, feats, 150.0)
+            os_, cs = of.sparse(), cf.sparse()
+            om, cm = os_.coordinate_manager, cs.coordinate_manager
+            ok, ck = os_.coordinate_map_key, cs.coordinate_map_key
+            for level in range(3):
+                nbr_c = cm.kernel_map_k3(ck)
+                lv = cm.level(ck)
+                maps[(mode, level)] = (nbr_c.cpu(), lv.masks_k3[0].cpu(), lv.masks_k3[1].cpu()[:27])
+                if mode == "blocks":
+                    assert np.array_equal(nbr_c.cpu().numpy().astype(np.int64), om.kernel_map_k3(ok)), f"level {level}"
+                    V = lv.V
+                    # row masks / counts are what the nbr table says
+                    pres = (nbr_c >= 0)
+                    want = (pres.long() << torch.arange(27, device="cuda")).sum(1).int()
+                    assert torch.equal(lv.masks_k3[0], want)
+                    assert torch.equal(lv.masks_k3[1][:27].long(), pres.sum(0))
+                    # keys and tile masks from the row masks == from the nbr table
+                    ws = torch.empty((128,), dtype=torch.uint8, device="cuda")
+                    k_old = torch.empty((V,), dtype=torch.int32, device="cuda")
+                    check(lib.b2me_mask_sort_keys(ptr(nbr_c), V, 27, ptr(k_old), ptr(ws), ws.numel(), stream()))
+                    k_new = torch.empty((V,), dtype=torch.int32, device="cuda")
+                    check(lib.b2me_mask_sort_keys_rows(ptr(lv.masks_k3[0]), ptr(lv.masks_k3[1]), V, 27, ptr(k_new), stream()))
+                    assert torch.equal(k_old, k_new)
+                    perm = torch.sort(k_new)[1].int()
+                    assert torch.equal(ME.tile_masks(nbr_c, perm, V, 27), ME.tile_masks(nbr_c, perm, V, 27, row_masks=lv.masks_k3[0]))
+                    assert torch.equal(ME.tile_masks(nbr_c, None, V, 27), ME.tile_masks(nbr_c, None, V, 27, row_masks=lv.masks_k3[0]))
+                ok, _ = om.stride_down(ok)
+                ck, _ = cm.stride_down(ck)
+        finally:
+            ME.set_k3_block_min_rows(65536)
+    for level in range(3):
+        for a, b in zip(maps[("blocks", level)], maps[("direct", level)]):
+            assert torch.equal(a, b), f"block path and direct path differ at level {level}"
+
+
 def test_sparse_collate_feeds_sparse_tensor():
     """a4 -> a5, the reference's training / test call pattern (data/alivev2.py:386-396 then test.py:52
     `ME.SparseTensor(feats, coordinates=coords, device=...)`): ragged samples with duplicates collated on the host,

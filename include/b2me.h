@@ -199,6 +199,10 @@ int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, i
 #define B2ME_TC_FLAG_NO_ROT128 2  /* 384-column tiles: one 384-column accumulator (round-1 layout) instead of the early
                                      release of the 256-column part + alternating 128-column regions; same results */
 
+#define B2ME_TC_FLAG_PF_BULK 4    /* L2 prefetch of the next offset's gathered rows by one cp.async.bulk.prefetch.L2 per row
+                                     instead of one prefetch.global.L2 per 128-byte chunk */
+#define B2ME_TC_FLAG_PF_NONE 8    /* no L2 prefetch (A/B) */
+
 /* V_in: rows of in1 (and of in2, which lies on the same coordinate map; with B2ME_TC_FLAG_TMA row indices outside
  * [0, V_in) read as zeros). op_dtype: type of in1 / in2 / packed_w (B2ME_BF16 | B2ME_TF32); residual rows are bf16
  * for bf16 operands and f32 for tf32 operands. out_dtype: B2ME_BF16 | B2ME_F32 (bf16 operands), B2ME_TF32 | B2ME_F32
@@ -305,8 +309,8 @@ int b2me_kabsch_batched(const double* ref, const double* tgt, const int32_t* npa
 
 /* ------------------------------------------------------------------------------------------------
  * K10: Open3D registration_icp(source=CAD, target=EE, max_corr, init, PointToPoint) as used by
- * utils/icp.py:50-81, batched over frames. One CTA per frame; exact nearest neighbour within
- * max_corr through a uniform grid over the frame's target points.
+ * utils/icp.py:50-81, batched over frames. ONE launch for all iterations: a thread-block cluster per frame keeps the
+ * frame's targets in shared memory; exact nearest neighbour within max_corr through a uniform grid over them.
  *   source_xyz [S,3] f32 (shared CAD cloud); target_xyz [T_total,3] f32, tgt_offsets [F+1] i32
  *   init_T [F,16] f64 row-major 4x4; out_T [F,16] f64; out_stats [F,4] f64 = fitness, inlier_rmse,
  *   iterations run, #correspondences
@@ -316,6 +320,7 @@ int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz
                          const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
                          double max_corr, int max_iter, double rel_fitness, double rel_rmse,
                          double* out_T, double* out_stats, void* ws, size_t ws_bytes,
+                         int cluster_size /* CTAs per frame: 1, 2, 4 or 8; 0 = as many as the source cloud fills */,
                          b2me_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

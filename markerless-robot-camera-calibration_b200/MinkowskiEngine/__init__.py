@@ -9,7 +9,7 @@ __version__ = "0.5.4+b200.0"
 from .core import (SparseTensor, TensorField, SparseTensorQuantizationMode, MinkowskiAlgorithm,  # noqa: F401
                    SparseTensorOperationMode, CoordinateManager, CoordinateMapKey, cat, set_compute_dtype,
                    get_compute_dtype, get_compute_mode, set_tc_operand_path, get_tc_operand_path,
-                   set_tc_rot128, set_fuse_head, reset_launch_count, launch_count, set_profile, set_mask_sort, set_mask_sort_block,
+                   set_tc_rot128, set_tc_prefetch, set_fuse_head, reset_launch_count, launch_count, set_profile, set_mask_sort, set_mask_sort_block,
                    set_mask_sort_two_level, set_k3_block_min_rows, set_mask_sort_morton, mask_sorted_perm, tile_masks)
 from .nn import *  # noqa: F401,F403
 from .nn import MinkowskiModuleBase  # noqa: F401

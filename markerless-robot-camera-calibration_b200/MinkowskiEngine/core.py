@@ -104,6 +104,13 @@ def set_tc_rot128(on):
     _State.tc_flags = (_State.tc_flags & ~_lib.TC_FLAG_NO_ROT128) | (0 if on else _lib.TC_FLAG_NO_ROT128)
 
 
+def set_tc_prefetch(mode):
+    """L2 prefetch of the next kernel offset's gathered rows in the tcgen05 convolution: "chunk" (default: one
+    prefetch.global.L2 per 128-byte chunk), "bulk" (one cp.async.bulk.prefetch.L2 per row) or "none"."""
+    bits = {"chunk": 0, "bulk": _lib.TC_FLAG_PF_BULK, "none": _lib.TC_FLAG_PF_NONE}[mode]
+    _State.tc_flags = (_State.tc_flags & ~(_lib.TC_FLAG_PF_BULK | _lib.TC_FLAG_PF_NONE)) | bits
+
+
 def set_fuse_head(on):
     """fused 256 -> 1024 -> C head in one launch (True, default) or the two-launch path with the hidden activation in
     HBM (False; A/B and parity tests)."""

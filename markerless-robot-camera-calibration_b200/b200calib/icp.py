@@ -105,7 +105,7 @@ def morton_sorted(source):
 
 
 def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD, max_iter=ICP_MAX_ITER,
-                    rel_fitness=ICP_REL_FITNESS, rel_rmse=ICP_REL_RMSE):
+                    rel_fitness=ICP_REL_FITNESS, rel_rmse=ICP_REL_RMSE, cluster_size=0):
     """source [S,3] f32 CUDA (CAD); targets [T_total,3] f32 CUDA; tgt_offsets [F+1]; init_T [F,4,4] f64.
     Returns (T [F,4,4] f64, stats [F,4] f64 = fitness, inlier_rmse, iterations, correspondences)."""
     source = morton_sorted(source.to(torch.float32).contiguous())
@@ -119,7 +119,8 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
     ws = torch.empty((lib.b2me_icp_workspace_bytes(targets.shape[0], F, source.shape[0]),), dtype=torch.uint8, device=dev)
     check(lib.b2me_icp_p2p_batched(ptr(source), source.shape[0], ptr(targets), ptr(offs), F, targets.shape[0],
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
-                                   ptr(out_T), ptr(stats), ptr(ws), ws.numel(), stream()), "icp_p2p_batched")
+                                   ptr(out_T), ptr(stats), ptr(ws), ws.numel(), int(cluster_size), stream()),
+          "icp_p2p_batched")
     _count(2)  # grid build + ONE persistent cluster launch for all evaluations
     return out_T.view(F, 4, 4), stats
 

@@ -544,7 +544,8 @@ k_icp_persistent(const float* __restrict__ src, int S, const int32_t* __restrict
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
                                     double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* out_T,
-                                    double* out_stats, void* ws, size_t ws_bytes, b2me_stream_t stream) {
+                                    double* out_stats, void* ws, size_t ws_bytes, int cluster_size,
+                                    b2me_stream_t stream) {
     if (!source_xyz || !tgt_offsets || !init_T || !out_T || !out_stats || !ws) return B2ME_EINVAL;
     if (!target_xyz && T_total > 0) return B2ME_EINVAL;  // an empty target cloud may come with a null pointer
     if (S <= 0 || F < 0 || T_total < 0 || max_iter < 0 || !(max_corr > 0)) return B2ME_EINVAL;
@@ -560,13 +561,18 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     // per-device attribute: set on every call (cheap) so that a process driving several GPUs works
     if (cudaFuncSetAttribute(k_icp_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return B2ME_ELAUNCH;
-    // cluster size: as many CTAs per frame as the SMs allow (1 CTA per SM at 200 KB of shared memory), at most one
-    // CTA per 512 source points
-    int dev = 0, sms = B2ME_NUM_SMS;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // cluster size (CTAs per frame). A frame's evaluation is as fast as its slice per CTA is short, and clusters are
+    // scheduled dynamically (a finished frame frees its SMs for a queued one), so the default is the widest cluster
+    // that still gives every CTA a full 512-point slice of the source cloud: a slowly converging frame then runs on 8
+    // SMs instead of holding 1-2 SMs for 30 iterations while the rest of the GPU idles (measured on the bench's 64
+    // frames: 2 CTAs per frame 28.9 ms).
     int csize = 1;
-    while (csize < ICP_MAX_CLUSTER && 2 * csize * F <= sms && 2 * csize * ICP_EVAL_THREADS <= S + ICP_EVAL_THREADS - 1)
-        csize *= 2;
+    if (cluster_size > 0) {
+        if (cluster_size > ICP_MAX_CLUSTER || (cluster_size & (cluster_size - 1))) return B2ME_EINVAL;
+        csize = cluster_size;
+    } else {
+        while (csize < ICP_MAX_CLUSTER && 2 * csize * ICP_EVAL_THREADS <= S) csize *= 2;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(F * csize), 1, 1);
     cfg.blockDim = dim3(ICP_EVAL_THREADS, 1, 1);

@@ -95,7 +95,10 @@ struct TcParams {
     uint8_t* head_argmax;  // [V_out] or null
     long long V_out;
     int Cin1, Cin2, nchunk1, nchunk2;
-    int Cout, n_tile, n_ntiles, stages;
+    int Cout, n_tile, n_ntiles;
+    int stages;    // A ring: gathered-row stages of 16 KB (= number of full / empty barriers)
+    int stages_b;  // B ring: weight stages of b_bytes (<= stages). The gathers come from DRAM (random rows, long
+                   // latency), the weights from L2: a short B ring leaves shared memory for a deep A ring
     int act, out_dtype, tmem_cols;
     int acc_bufs;  // 2 when two accumulators fit TMEM (2 n_tile <= 512): the epilogue overlaps the next tile's MMAs
     int rot128;    // n_tile = 384: 256-column part released early, 128-column part alternates between two regions
@@ -105,6 +108,8 @@ struct TcParams {
     int n_pairs;  // 256-row tile pairs
     int debug;    // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
     int tma;      // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
+    int pf_mode;  // L2 prefetch of the next offset's rows: 0 prefetch.global.L2 per 128-byte chunk, 1 one
+                  // cp.async.bulk.prefetch.L2 per row (all its chunks), 2 none
     // tensor maps (TMA mode): the two sources as [V_in, Cin] with a (128-byte chunk) x 1-row box (SWIZZLE_128B; rows are
     // picked by tile::gather4, absent neighbours (-1) and channels past Cin are out of bounds = zero-filled) and the
     // packed weights as 128-byte rows (box = one CTA's half of an item, no swizzle: the image is pre-swizzled)
@@ -176,6 +181,10 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// bulk (TMA engine) prefetch of `bytes` contiguous bytes into L2; address and size multiples of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -362,16 +371,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     constexpr int EPP = 16 / ES;     // channels per 16-byte piece
     constexpr int KSTEP = 32 / ES;   // channels per MMA (32 bytes of K)
 
-    const int S = p.stages;
-    const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
+    const int S = p.stages, SB = p.stages_b;
+    const uint32_t b_ring = base + (uint32_t)S * TC_A_BYTES;   // B ring follows the A ring
     const int tid = threadIdx.x;
     // shfl-broadcast: the compiler then knows the warp index (hence every role branch) is warp-uniform
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
-    // carve: [stages][nbr_s 128*KT i32][scale Cout][shift Cout][head W2 Cout*head_cp][epilogue staging 8 x 2 KB]
+    // carve: [A ring S x 16 KB][B ring SB x b_bytes][nbr_s 128*KT i32][scale Cout][shift Cout][head W2 Cout*head_cp][epilogue staging 8 x 2 KB]
     //        [barriers][tmem ptr]
-    uint32_t off = (uint32_t)S * stage_bytes;
+    uint32_t off = (uint32_t)S * TC_A_BYTES + (uint32_t)SB * p.b_bytes;
     int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
     off += TC_BM * KT * 4;
     off = (off + 15u) & ~15u;
@@ -471,23 +480,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 if ((m & (m - 1u)) == 0u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH) {
+                } else if (TC_L2_PREFETCH && p.pf_mode != 2) {
                     // pull the rows of the NEXT offset into L2 one whole offset (= nchunk items) ahead of their gather
                     const uint32_t m2 = m & (m - 1u);
                     const int k2 = __ffs((int)m2) - 1;
                     const int id2 = nbr_s[(32 * warp + lane) * KT + k2];
                     if (id2 >= 0) {
-                        for (int ch = 0; ch < p.nchunk1; ++ch)
-                            prefetch_l2(p.in1 + ((long long)id2 * p.Cin1 + ch * CPC) * ES);
-                        for (int ch = 0; ch < p.nchunk2; ++ch)
-                            prefetch_l2(p.in2 + ((long long)id2 * p.Cin2 + ch * CPC) * ES);
+                        if (p.pf_mode == 1) {
+                            prefetch_l2_bulk(p.in1 + (long long)id2 * p.Cin1 * ES, (uint32_t)(p.Cin1 * ES));
+                            if (p.nchunk2) prefetch_l2_bulk(p.in2 + (long long)id2 * p.Cin2 * ES, (uint32_t)(p.Cin2 * ES));
+                        } else {
+                            for (int ch = 0; ch < p.nchunk1; ++ch)
+                                prefetch_l2(p.in1 + ((long long)id2 * p.Cin1 + ch * CPC) * ES);
+                            for (int ch = 0; ch < p.nchunk2; ++ch)
+                                prefetch_l2(p.in2 + ((long long)id2 * p.Cin2 + ch * CPC) * ES);
+                        }
                     }
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
                     mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u);
                     if (tc_elect_one()) {
-                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes + (uint32_t)(32 * warp) * 128u;
+                        const uint32_t a_s = base + (uint32_t)ist * TC_A_BYTES + (uint32_t)(32 * warp) * 128u;
                         const CUtensorMap* tm = c < p.nchunk1 ? &p.tm_in1 : &p.tm_in2;
                         const int col = (c < p.nchunk1 ? c : c - p.nchunk1) * CPC;
 #pragma unroll
@@ -524,7 +538,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH) {
+                } else if (TC_L2_PREFETCH && p.pf_mode == 0) {
                     // the gathered rows come from all over the tensor (DRAM latency >> the ring's depth in time): pull
                     // the rows of the NEXT offset into L2 now, one whole offset (= nchunk items) ahead of their gather.
                     // lane j takes the 128-byte chunks j, j + 8, ... of each of this thread's 8 rows.
@@ -540,6 +554,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                             if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
                         }
                     }
+                } else if (TC_L2_PREFETCH && p.pf_mode == 1) {
+                    // the same through the bulk-copy engine: ONE prefetch per row and source covering all its chunks
+                    // (thread t of the 128 producers takes row t of the tile)
+                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
+                    const int id = nbr_s[tid * KT + k2];
+                    if (id >= 0) {
+                        prefetch_l2_bulk(p.in1 + (long long)id * p.Cin1 * ES, (uint32_t)(p.Cin1 * ES));
+                        if (p.nchunk2) prefetch_l2_bulk(p.in2 + (long long)id * p.Cin2 * ES, (uint32_t)(p.Cin2 * ES));
+                    }
                 }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c) {
@@ -551,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * CPC; }
                     const int kw = min(CPC, cin - coff);
                     if (j * EPP < kw && !(p.debug & 1)) {
-                        const uint32_t a_s = base + (uint32_t)ist * stage_bytes;
+                        const uint32_t a_s = base + (uint32_t)ist * TC_A_BYTES;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = rbase + 16 * i;
@@ -590,8 +613,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             const int ks_last2 = p.nchunk2 ? (p.Cin2 - (p.nchunk2 - 1) * CPC) / KSTEP : 0;
             // low words of the SWIZZLE_128B K-major descriptors of stage 0 (high word is constant, see tc_mma_lo)
             const uint32_t a_lo0 = ((base >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t stage_lo = stage_bytes >> 4;
-            const uint32_t b_off_lo = TC_A_BYTES >> 4, b2_off_lo = (TC_A_BYTES + (uint32_t)(n_a >> 1) * 128u) >> 4;
+            const uint32_t b_lo0 = ((b_ring >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t a_stage_lo = TC_A_BYTES >> 4, b_stage_lo = p.b_bytes >> 4;
+            const uint32_t b2_off_lo = ((uint32_t)(n_a >> 1) * 128u) >> 4;   // second instruction's rows inside a B stage
+            int sb = 0;                                                        // B stage of the current item
             const bool need_fence = !p.tma;  // cp.async (generic proxy) writes of A -> visible to the MMA (async proxy)
             int st = 0, ph = 0;
             PROF_DECL
@@ -638,15 +663,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         pt_ = clock64();
 #endif
                         tc_fence_after();
-                        const uint32_t a_lo = a_lo0 + (uint32_t)st * stage_lo;
+                        const uint32_t a_lo = a_lo0 + (uint32_t)st * a_stage_lo;
+                        const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
                         if (tc_elect_one()) {
                             if (need_fence) fence_proxy_async();
                             // the two instructions of a K step share the A slice; both read it from shared memory
                             // (keeping it in the collector buffer, collector::a::fill / lastuse, was measured slower)
                             for (int kk = 0; kk < ks; ++kk) {
-                                tc_mma_lo<ES>(tmem_acc, a_lo + 2u * kk, a_lo + b_off_lo + 2u * kk, idesc_a, acc);
+                                tc_mma_lo<ES>(tmem_acc, a_lo + 2u * kk, b_lo + 2u * kk, idesc_a, acc);
                                 if (n_b)
-                                    tc_mma_lo<ES>(tmem_acc_b, a_lo + 2u * kk, a_lo + b2_off_lo + 2u * kk, idesc_b, acc);
+                                    tc_mma_lo<ES>(tmem_acc_b, a_lo + 2u * kk, b_lo + b2_off_lo + 2u * kk, idesc_b, acc);
                                 acc = 1u;
                             }
                             tc_commit_pair(bar_empty + 8 * st);  // frees the stage in both CTAs
@@ -654,6 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         acc = ks > 0 ? 1u : acc;
                         __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
+                        if (++sb == SB) sb = 0;
 #ifdef B2ME_TC_PROFILE
                         prof_[5] += (unsigned long long)(clock64() - pt_);
 #endif
@@ -697,7 +724,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
         }
     } else if (warp == 5) {
         // =============================== weight (B) loader ===============================
-        int st = 0, ph = 0;
+        // item i announces its bytes on full[i % S] (the item's A stage) and lands in B stage i % SB, which is free once
+        // item i - SB has been consumed: the loader follows the empty barriers with a cursor SB items behind its own
+        int st = 0, sb = 0;            // A stage (full barrier) / B stage of the item being loaded
+        int wst = 0, wph = 0, lag = 0; // cursor of the item whose consumption frees this B stage
         const uint32_t full_leader = mapa_u32(bar_full, 0u);
         uint32_t kmask_next = unit0 < p.n_pairs ? pair_mask(unit0) : 0u;
         for (int it = 0;; ++it) {
@@ -709,9 +739,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             for (int k = 0; k < KT; ++k) {
                 if (!((kmask >> k) & 1u)) continue;
                 for (int c = 0; c < nchunk; ++c) {
-                    mbar_wait(bar_empty + 8 * st, (uint32_t)ph ^ 1u);
+                    if (lag == SB) {   // item (this - SB) consumed -> its B stage (= this item's) is free
+                        mbar_wait(bar_empty + 8 * wst, (uint32_t)wph);
+                        if (++wst == S) { wst = 0; wph ^= 1; }
+                    } else {
+                        ++lag;
+                    }
                     if (lane == 0) {
-                        const uint32_t b_s = base + (uint32_t)st * stage_bytes + TC_A_BYTES;
+                        const uint32_t b_s = b_ring + (uint32_t)sb * p.b_bytes;
                         const long long item = ((long long)nt * KT + k) * nchunk + c;
                         if (p.tma) {
                             // leader: one arrive announcing all four transfers of the stage (A and B of both CTAs)
@@ -727,7 +762,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         }
                     }
                     __syncwarp();
-                    if (++st == S) { st = 0; ph ^= 1; }
+                    if (++st == S) st = 0;
+                    if (++sb == SB) sb = 0;
                 }
             }
         }
@@ -1375,23 +1411,31 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
 
     const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 + head_bytes + 16 +
                          (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 16 + 16 + 24 + 16;
-    const size_t stage_bytes = (size_t)TC_A_BYTES + p.b_bytes;
+    // B ring: 3 stages of weights (L2-resident, short latency; A/B override in flags bits 8-10), A ring: as many
+    // 16 KB stages of gathered rows (DRAM, long latency) as the rest of shared memory holds
+    int SB = (flags >> 8) & 7;
+    if (SB == 0) SB = 3;
+    if (SB < 2) SB = 2;
     int S = TC_MAX_STAGES;
-    while (S >= 2 && fixed + (size_t)S * stage_bytes > TC_MAX_SMEM) --S;
+    while (S >= 2 && fixed + (size_t)S * TC_A_BYTES + (size_t)(SB < S ? SB : S) * p.b_bytes > TC_MAX_SMEM) --S;
     if (S < 2) return B2ME_EUNSUPPORTED;
+    if (SB > S) SB = S;
     p.debug = 0;
 #if defined(B2ME_TC_PROFILE) || defined(B2ME_TC_EXPERIMENT)
     if (const char* e = getenv("B2ME_TC_DEBUG")) p.debug = atoi(e);
     if (const char* e = getenv("B2ME_TC_STAGES")) {  // debug build only: ring-depth experiments
         const int want = atoi(e);
         if (want >= 2 && want < S) S = want;
+        if (SB > S) SB = S;
     }
 #endif
     p.stages = S;
+    p.stages_b = SB;
     // B2ME_TC_FLAG_TMA routes the operands through the TMA unit (tile::gather4 rows + 2-D weight boxes completing on
     // the leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
     // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms), so it is an alternative the caller picks
     // per call; the parity tests run both.
+    p.pf_mode = (flags & B2ME_TC_FLAG_PF_NONE) ? 2 : ((flags & B2ME_TC_FLAG_PF_BULK) ? 1 : 0);
     p.tma = 0;
     if ((flags & B2ME_TC_FLAG_TMA) && V_in > 0) {
         const uint64_t w_rows = (uint64_t)K * (p.nchunk1 + p.nchunk2) * (uint64_t)Cout;
@@ -1405,7 +1449,7 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
         if (!ok) return B2ME_ELAUNCH;
         p.tma = 1;
     }
-    size_t smem = fixed + (size_t)S * stage_bytes;
+    size_t smem = fixed + (size_t)S * TC_A_BYTES + (size_t)SB * p.b_bytes;
     if (smem < TC_MIN_SMEM) smem = TC_MIN_SMEM;
 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

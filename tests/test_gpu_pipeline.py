@@ -253,3 +253,37 @@ def test_predict_batch_sanity_check_wiring(setup):
         assert len(res[f].key_points) == len(kps)
         seen += 1
     assert seen >= 2
+
+
+def test_predict_stream_matches_sequential(setup):
+    """BatchedInferenceEngine.predict_stream (batches in flight on their own streams / host threads) returns, in batch
+    order, exactly what predict_device returns for each batch alone (every kernel is deterministic; the library keeps no
+    per-call state)."""
+    ME, o, c, frames = setup
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig, batch_frames
+    cad = ee_surface_cloud(1024, 13)
+    eng = BatchedInferenceEngine(c["seg"], c["rot"], c["kp"], cad_points=torch.from_numpy(cad).cuda(),
+                                 config=PipelineConfig(seg_scale=100.0, rot_scale=200.0, kp_scale=400.0,
+                                                       ee_point_counts_threshold=128, kp_conf_threshold=0.0,
+                                                       sanity_min_ee_points=128))
+    ME.set_compute_dtype(torch.bfloat16)
+    try:
+        batches = []
+        for sel in ([0, 1], [2], [1, 2, 0]):
+            fr = [(frames[i]["points"], frames[i]["rgb"]) for i in sel]
+            pts, rgb, bidx, offs = batch_frames(fr, torch.device("cuda"))
+            gl = torch.as_tensor(np.concatenate([frames[i]["labels"] for i in sel]).astype(np.uint8)).cuda()
+            batches.append((pts, rgb, bidx, offs, None, gl))
+        torch.cuda.synchronize()
+        seq = [eng.predict_device(*b) for b in batches]
+        for depth in (1, 2):
+            got = list(eng.predict_stream(batches, depth=depth))
+            torch.cuda.synchronize()
+            assert len(got) == len(seq)
+            for (l0, p0), (l1, p1) in zip(seq, got):
+                assert torch.equal(l0, l1)
+                assert np.array_equal(p0["ok_frames"], p1["ok_frames"])
+                assert np.array_equal(p0["ee_T"], p1["ee_T"]) and np.array_equal(p0["confident"], p1["confident"])
+                assert np.array_equal(p0["kp_T"], p1["kp_T"], equal_nan=True)
+    finally:
+        ME.set_compute_dtype(torch.float32)

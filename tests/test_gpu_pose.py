@@ -66,3 +66,31 @@ def test_icp_edge_cases(cad_points):
     assert torch.allclose(T.cpu()[0], T0[0])
     same, _ = icp_p2p_batched(cad, cad.clone(), [0, len(cad_points)], T0)     # identical clouds: identity
     assert torch.allclose(same.cpu()[0], T0[0], atol=1e-9)
+
+
+def test_icp_cluster_sizes_agree(cad_points):
+    """k_icp_persistent with 1, 2, 4 or 8 CTAs per frame (thread-block cluster sharing one frame): same iteration
+    count, poses equal to fp64 summation-order noise (the per-CTA partial sums are added in rank order)."""
+    from b200calib.icp import icp_p2p_batched
+    rng = np.random.default_rng(3)
+    cad = cad_points.astype(np.float32)
+    tgs, offs, T0 = [], [0], []
+    for f in range(5):
+        ang = rng.uniform(-0.5, 0.5)
+        T = np.eye(4)
+        T[:3, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+        T[:3, 3] = rng.uniform(-0.3, 0.3, 3) + [0, 0, 1.2]
+        sel = cad[rng.permutation(len(cad))[:1500 + 500 * f]].astype(np.float64)
+        tgs.append((sel @ T[:3, :3].T + T[:3, 3] + rng.normal(0, 0.001, sel.shape)).astype(np.float32))
+        offs.append(offs[-1] + len(sel))
+        init = T.copy()
+        init[:3, 3] += rng.uniform(-0.02, 0.02, 3)
+        T0.append(init)
+    cad_d, tg_d = torch.from_numpy(cad).cuda(), torch.from_numpy(np.concatenate(tgs)).cuda()
+    T0 = torch.from_numpy(np.stack(T0))
+    ref_T, ref_st = icp_p2p_batched(cad_d, tg_d, offs, T0, cluster_size=1)
+    for cs in (2, 4, 8, 0):
+        T, st = icp_p2p_batched(cad_d, tg_d, offs, T0, cluster_size=cs)
+        assert torch.equal(st[:, 2], ref_st[:, 2]), f"iteration counts differ at cluster size {cs}"
+        assert float((T - ref_T).abs().max()) < 1e-9
+        assert float((st[:, :2] - ref_st[:, :2]).abs().max()) < 1e-9

@@ -78,6 +78,9 @@ def parse():
     ap.add_argument("--cprofile", default=None, help="one extra (untimed) step under cProfile: host-side launch cost (text)")
     ap.add_argument("--torch-profile", default=None,
                     help="one extra (untimed) step under torch.profiler: per-kernel device times + GPU busy fraction (text)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="one extra device-resident step between cudaProfilerStart / Stop at the end (ncu "
+                         "--profile-from-start off then captures exactly one warm step)")
     ap.add_argument("--conv-table", default=None, help="write the per-convolution census + CUDA-event times here (JSON)")
     ap.add_argument("--report", default=None, help="write the evaluation record of the last step here (JSON)")
     return ap.parse_args()
@@ -482,6 +485,13 @@ def run_b200(args, rank, world, local):
         step_device()
         stage_ms = {k: round(v, 3) for k, v in eng.stage_times.items()}
         eng.stage_times = None
+
+    if args.profile_range and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     if args.cprofile and rank == 0:
         # developer aid: where the HOST spends its time while launching one step (the GPU idles when it falls behind)

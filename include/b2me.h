@@ -202,6 +202,8 @@ int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, i
 #define B2ME_TC_FLAG_PF_BULK 4    /* L2 prefetch of the next offset's gathered rows by one cp.async.bulk.prefetch.L2 per row
                                      instead of one prefetch.global.L2 per 128-byte chunk */
 #define B2ME_TC_FLAG_PF_NONE 8    /* no L2 prefetch (A/B) */
+#define B2ME_TC_FLAG_PF_NEAR 16   /* L2 prefetch of the NEXT offset only (default: two offsets ahead, and the first two
+                                     offsets of a tile a whole tile ahead) */
 
 /* V_in: rows of in1 (and of in2, which lies on the same coordinate map; with B2ME_TC_FLAG_TMA row indices outside
  * [0, V_in) read as zeros). op_dtype: type of in1 / in2 / packed_w (B2ME_BF16 | B2ME_TF32); residual rows are bf16

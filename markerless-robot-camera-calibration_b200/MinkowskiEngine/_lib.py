@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2ME_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libb2me.so")
 
 F32, BF16, TF32 = 0, 1, 2
-TC_FLAG_TMA, TC_FLAG_NO_ROT128, TC_FLAG_PF_BULK, TC_FLAG_PF_NONE = 1, 2, 4, 8
+TC_FLAG_TMA, TC_FLAG_NO_ROT128, TC_FLAG_PF_BULK, TC_FLAG_PF_NONE, TC_FLAG_PF_NEAR = 1, 2, 4, 8, 16
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 _vp, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double

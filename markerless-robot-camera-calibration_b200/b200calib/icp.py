@@ -121,7 +121,10 @@ def icp_p2p_batched(source, targets, tgt_offsets, init_T, max_corr=ICP_THRESHOLD
                                    ptr(init_T), float(max_corr), int(max_iter), float(rel_fitness), float(rel_rmse),
                                    ptr(out_T), ptr(stats), ptr(ws), ws.numel(), int(cluster_size), stream()),
           "icp_p2p_batched")
-    _count(2)  # grid build + ONE persistent cluster launch for all evaluations
+    # grid build + ONE persistent launch for all evaluations (at least as many frames as SMs, or an explicit cluster
+    # size), else one launch per evaluation (the library's dispatch rule, b2me_icp_p2p_batched)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    _count(2 if (cluster_size > 0 or F >= sms) else 2 + int(max_iter))
     return out_T.view(F, 4, 4), stats
 
 

@@ -514,25 +514,36 @@ k_kernel_map_k3_blocks(const int4* __restrict__ coords, int64_t V, int ts, int s
             }
             brow_s[combo][tid] = r;
         }
+        // per (dy, dz): the 4-cell x-row of the block that holds the neighbours' y / z (ONE 16-byte load), plus one cell
+        // of the x-adjacent block when the voxel sits on an x face of its block: 9..18 loads instead of 26
+        const int lx = li[0];
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            const int d[3] = {k % 3 - 1, (k / 3) % 3 - 1, k / 9 - 1};
-            int combo = 0, l = 0;
+        for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const int n = li[a] + d[a];
-                combo |= ((n < 0 || n > 3) ? 1 : 0) << a;
-                l |= (n & 3) << (2 * a);
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int ny = li[1] + dy, nz = li[2] + dz;
+                const int cyz = (((ny < 0 || ny > 3) ? 1 : 0) << 1) | (((nz < 0 || nz > 3) ? 1 : 0) << 2);
+                const int row = ((ny & 3) << 2) | ((nz & 3) << 4);
+                const uint32_t B0 = brow_s[cyz][tid];
+                int4 cells = make_int4(-1, -1, -1, -1);
+                if (B0 != 0xFFFFFFFFu) cells = __ldg(reinterpret_cast<const int4*>(brows + (int64_t)B0 * 64 + row));
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int k = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+                    const int nx = lx + dx;
+                    int32_t r;
+                    if (k == 13) {
+                        r = (int32_t)v;
+                    } else if (nx >= 0 && nx <= 3) {
+                        r = nx == 0 ? cells.x : (nx == 1 ? cells.y : (nx == 2 ? cells.z : cells.w));
+                    } else {
+                        const uint32_t B1 = brow_s[cyz | 1][tid];
+                        r = (B1 == 0xFFFFFFFFu) ? -1 : __ldg(brows + (int64_t)B1 * 64 + row + (nx & 3));
+                    }
+                    res_s[tid * 27 + k] = r;
+                    m |= (r >= 0 ? 1u : 0u) << k;
+                }
             }
-            int32_t r;
-            if (k == 13) {
-                r = (int32_t)v;
-            } else {
-                const uint32_t B = brow_s[combo][tid];
-                r = (B == 0xFFFFFFFFu) ? -1 : __ldg(brows + (int64_t)B * 64 + l);
-            }
-            res_s[tid * 27 + k] = r;
-            m |= (r >= 0 ? 1u : 0u) << k;
         }
         row_masks[v] = m;
     }

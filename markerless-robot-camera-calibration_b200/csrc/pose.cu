@@ -541,6 +541,108 @@ k_icp_persistent(const float* __restrict__ src, int S, const int32_t* __restrict
     }
 }
 
+// Multi-launch variant for FEW frames (fewer than the GPU has SMs): one launch per evaluation over (source chunks of
+// 512 x frames). The (frame, chunk) CTAs of all live frames are scheduled dynamically over all SMs, so the slowly
+// converging / expensive frames (bad initial pose: every query scans most of the targets) spread over the whole GPU
+// instead of pinning one cluster each; the last CTA of a frame (atomic ticket) adds the chunk slots in chunk order and
+// runs the update. A frame that is done returns immediately. Measured on the bench's 64 frames (32 crops x 2 initial
+// poses, half of them far off): 13.5 ms against 22.7-28.9 ms for the persistent kernel; with 1 000 frames the
+// persistent kernel wins (140 ms against 31 launches of 8 000 CTAs each).
+__global__ void __launch_bounds__(ICP_EVAL_THREADS)
+k_icp_eval(const float* __restrict__ src, int S, const int32_t* __restrict__ tgt_offsets,
+           const IcpFrameGrid* __restrict__ grids, const int32_t* __restrict__ cell_start_all,
+           const float4* __restrict__ sorted, int32_t* __restrict__ match_all, IcpState* __restrict__ state,
+           double* __restrict__ partial_all,
+           int ev, int tcap, double max_corr, int max_iter, double rel_fitness, double rel_rmse,
+           double* __restrict__ out_T, double* __restrict__ out_stats) {
+    extern __shared__ __align__(16) unsigned char icp_smem[];
+    float4* tg_s = reinterpret_cast<float4*>(icp_smem);
+    int* cs = reinterpret_cast<int*>(icp_smem + (size_t)tcap * sizeof(float4));
+    __shared__ double T_s[12];
+    __shared__ double red[ICP_EVAL_THREADS / 32][ICP_NSUM];
+    __shared__ double tot[ICP_NSUM];
+    __shared__ IcpFrameGrid g;
+    __shared__ int last_s;
+    const int f = blockIdx.y;
+    const int nchunk = gridDim.x;
+    IcpState* st = state + f;
+    if (st->done) return;  // uniform for the CTA; written only by the frame's last CTA of an earlier launch
+    const int t0 = tgt_offsets[f];
+    const int nT = tgt_offsets[f + 1] - t0;
+    if (threadIdx.x < 12) T_s[threadIdx.x] = st->T[threadIdx.x];
+    if (threadIdx.x == 0) g = grids[f];
+    __syncthreads();
+    const int ncell = g.dims[0] * g.dims[1] * g.dims[2];
+    {
+        const int32_t* cell_start = cell_start_all + (int64_t)f * (ICP_CELLS + 1);
+        for (int c = threadIdx.x; c <= ncell; c += blockDim.x) cs[c] = cell_start[c];
+    }
+    const bool in_smem = nT <= tcap;
+    if (in_smem)
+        for (int i = threadIdx.x; i < nT; i += blockDim.x) tg_s[i] = __ldg(sorted + t0 + i);
+    __syncthreads();
+    const double R2 = max_corr * max_corr;
+    double acc[ICP_NSUM];
+#pragma unroll
+    for (int q = 0; q < ICP_NSUM; ++q) acc[q] = 0.0;
+    if (nT > 0) {
+        int32_t* match = match_all + (int64_t)f * S;
+        for (int i = blockIdx.x * ICP_EVAL_THREADS + threadIdx.x; i < S; i += nchunk * ICP_EVAL_THREADS) {
+            const double sx = src[i * 3], sy = src[i * 3 + 1], sz = src[i * 3 + 2];
+            const double px = T_s[0] * sx + T_s[1] * sy + T_s[2] * sz + T_s[3];
+            const double py = T_s[4] * sx + T_s[5] * sy + T_s[6] * sz + T_s[7];
+            const double pz = T_s[8] * sx + T_s[9] * sy + T_s[10] * sz + T_s[11];
+            double best, bx = 0, by = 0, bz = 0;
+            int best_j, best_s;
+            const int seed = ev > 0 ? match[i] : -1;
+            if (in_smem) icp_search<true>(tg_s, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+            else icp_search<false>(sorted + t0, cs, g, px, py, pz, R2, seed, best, best_j, best_s, bx, by, bz);
+            match[i] = best_s;
+            if (best_j != 0x7FFFFFFF) {
+                acc[0] += 1.0; acc[1] += best;
+                acc[2] += px; acc[3] += py; acc[4] += pz;
+                acc[5] += bx; acc[6] += by; acc[7] += bz;
+                acc[8] += px * bx;  acc[9] += px * by;  acc[10] += px * bz;
+                acc[11] += py * bx; acc[12] += py * by; acc[13] += py * bz;
+                acc[14] += pz * bx; acc[15] += pz * by; acc[16] += pz * bz;
+            }
+        }
+    }
+    // fixed-order block reduction -> this chunk's slot
+#pragma unroll
+    for (int q = 0; q < ICP_NSUM; ++q) {
+        double v = acc[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    double* partial = partial_all + (int64_t)f * ICP_MAX_CHUNKS * ICP_NSUM;
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0.0;
+        for (int wv = 0; wv < ICP_EVAL_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        partial[blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&st->counter, 1u);
+        last_s = (ticket == (unsigned int)(nchunk - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!last_s) return;
+    // ---- last CTA of the frame: chunk slots in chunk order, convergence test, Kabsch update
+    __threadfence();
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0.0;
+        for (int c = 0; c < nchunk; ++c) v += __ldcg(partial + c * ICP_NSUM + threadIdx.x);
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        icp_frame_update(st, tot, T_s, f, S, ev, max_iter, rel_fitness, rel_rmse, out_T, out_stats);
+}
+
+
 extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float* target_xyz,
                                     const int32_t* tgt_offsets, int F, int64_t T_total, const double* init_T,
                                     double max_corr, int max_iter, double rel_fitness, double rel_rmse, double* out_T,
@@ -558,21 +660,32 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
                                                          w.cell_start, w.cell_cursor, w.sorted);
     const size_t smem = ICP_EVAL_SMEM;
     const int tcap = (int)((smem - (size_t)(ICP_CELLS + 1) * sizeof(int)) / sizeof(float4));
+    int dev = 0, sms = B2ME_NUM_SMS;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cluster_size < 0 || cluster_size > ICP_MAX_CLUSTER || (cluster_size & (cluster_size - 1))) return B2ME_EINVAL;
+    // cluster_size 0 = automatic: at least as many frames as SMs -> persistent kernel, one CTA per frame (frames are
+    // scheduled dynamically, every thread takes S / 512 queries per evaluation: the heavy-tailed query costs average
+    // out); fewer frames -> one launch per evaluation with (frame, chunk) CTAs balanced over all SMs.
+    const bool persistent = cluster_size > 0 || F >= sms;
+    if (!persistent) {
+        int nchunk = (S + ICP_EVAL_THREADS - 1) / ICP_EVAL_THREADS;
+        if (nchunk > ICP_MAX_CHUNKS) nchunk = ICP_MAX_CHUNKS;
+        if (F > 65535) return B2ME_EUNSUPPORTED;  // gridDim.y
+        if (cudaFuncSetAttribute(k_icp_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return B2ME_ELAUNCH;
+        const dim3 grid((unsigned)nchunk, (unsigned)F);
+        // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
+        for (int ev = 0; ev <= max_iter; ++ev)
+            k_icp_eval<<<grid, ICP_EVAL_THREADS, smem, s>>>(source_xyz, S, tgt_offsets, w.grids, w.cell_start, w.sorted,
+                                                            w.match, w.state, w.partial, ev, tcap, max_corr, max_iter,
+                                                            rel_fitness, rel_rmse, out_T, out_stats);
+        B2ME_CHECK_LAUNCH();
+        return B2ME_OK;
+    }
     // per-device attribute: set on every call (cheap) so that a process driving several GPUs works
     if (cudaFuncSetAttribute(k_icp_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return B2ME_ELAUNCH;
-    // cluster size (CTAs per frame). A frame's evaluation is as fast as its slice per CTA is short, and clusters are
-    // scheduled dynamically (a finished frame frees its SMs for a queued one), so the default is the widest cluster
-    // that still gives every CTA a full 512-point slice of the source cloud: a slowly converging frame then runs on 8
-    // SMs instead of holding 1-2 SMs for 30 iterations while the rest of the GPU idles (measured on the bench's 64
-    // frames: 2 CTAs per frame 28.9 ms).
-    int csize = 1;
-    if (cluster_size > 0) {
-        if (cluster_size > ICP_MAX_CLUSTER || (cluster_size & (cluster_size - 1))) return B2ME_EINVAL;
-        csize = cluster_size;
-    } else {
-        while (csize < ICP_MAX_CLUSTER && 2 * csize * ICP_EVAL_THREADS <= S) csize *= 2;
-    }
+    const int csize = cluster_size > 0 ? cluster_size : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(F * csize), 1, 1);
     cfg.blockDim = dim3(ICP_EVAL_THREADS, 1, 1);
@@ -585,7 +698,6 @@ extern "C" int b2me_icp_p2p_batched(const float* source_xyz, int S, const float*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // evaluation 0 uses init; then for it = 1..max_iter: update from the last evaluation, evaluate, test convergence
     if (cudaLaunchKernelEx(&cfg, k_icp_persistent, source_xyz, S, tgt_offsets, (const IcpFrameGrid*)w.grids,
                            (const int32_t*)w.cell_start, (const float4*)w.sorted, w.match, w.state, w.partial, tcap,
                            max_corr, max_iter, rel_fitness, rel_rmse, out_T, out_stats) != cudaSuccess)

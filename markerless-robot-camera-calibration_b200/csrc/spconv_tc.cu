@@ -108,8 +108,9 @@ struct TcParams {
     int n_pairs;  // 256-row tile pairs
     int debug;    // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
     int tma;      // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
-    int pf_mode;  // L2 prefetch of the next offset's rows: 0 prefetch.global.L2 per 128-byte chunk, 1 one
-                  // cp.async.bulk.prefetch.L2 per row (all its chunks), 2 none
+    int pf_mode;  // L2 prefetch of later offsets' rows: 0 prefetch.global.L2 per 128-byte chunk two offsets ahead + the
+                  // first two offsets of a tile by the kernel-map warps, 1 one cp.async.bulk.prefetch.L2 per row of the
+                  // next offset, 2 none, 3 per chunk for the next offset only (round-1 scheme)
     // tensor maps (TMA mode): the two sources as [V_in, Cin] with a (128-byte chunk) x 1-row box (SWIZZLE_128B; rows are
     // picked by tile::gather4, absent neighbours (-1) and channels past Cin are out of bounds = zero-filled) and the
     // packed weights as 128-byte rows (box = one CTA's half of an item, no swizzle: the image is pre-swizzled)
@@ -481,10 +482,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
                 } else if (TC_L2_PREFETCH && p.pf_mode != 2) {
-                    // pull the rows of the NEXT offset into L2 one whole offset (= nchunk items) ahead of their gather
-                    const uint32_t m2 = m & (m - 1u);
-                    const int k2 = __ffs((int)m2) - 1;
-                    const int id2 = nbr_s[(32 * warp + lane) * KT + k2];
+                    // pull the rows of a later offset into L2 (mode 0: two offsets ahead, see the cp.async producers)
+                    uint32_t m2 = m & (m - 1u);
+                    if (p.pf_mode == 0) m2 &= m2 - 1u;
+                    const int k2 = m2 ? __ffs((int)m2) - 1 : 0;
+                    const int id2 = m2 ? nbr_s[(32 * warp + lane) * KT + k2] : -1;
                     if (id2 >= 0) {
                         if (p.pf_mode == 1) {
                             prefetch_l2_bulk(p.in1 + (long long)id2 * p.Cin1 * ES, (uint32_t)(p.Cin1 * ES));
@@ -538,20 +540,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH && p.pf_mode == 0) {
-                    // the gathered rows come from all over the tensor (DRAM latency >> the ring's depth in time): pull
-                    // the rows of the NEXT offset into L2 now, one whole offset (= nchunk items) ahead of their gather.
+                } else if (TC_L2_PREFETCH && (p.pf_mode == 0 || p.pf_mode == 3)) {
+                    // the gathered rows come from all over the tensor (DRAM latency, and its tail: a stage is full only
+                    // when the slowest of its 256 rows has landed, >> the ring's depth in time): pull the rows of a
+                    // LATER offset into L2 now. Mode 0: the offset after the next one (two offsets = 2 nchunk items
+                    // ahead; the first two offsets of a tile are prefetched by the kernel-map warps a whole tile
+                    // ahead), mode 3: the next offset (round-1 scheme).
                     // lane j takes the 128-byte chunks j, j + 8, ... of each of this thread's 8 rows.
-                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
-                    for (int cj = j; cj < nchunk; cj += 8) {
-                        const uint8_t* psrc;
-                        int pcin, pcoff;
-                        if (cj < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = cj * CPC; }
-                        else { psrc = p.in2; pcin = p.Cin2; pcoff = (cj - p.nchunk1) * CPC; }
+                    uint32_t later = kmask >> (k + 1);                 // offsets after k (non-zero here)
+                    if (p.pf_mode == 0) later &= later - 1u;           // drop the next one
+                    if (later != 0u) {
+                        const int k2 = k + 1 + __ffs((int)later) - 1;
+                        for (int cj = j; cj < nchunk; cj += 8) {
+                            const uint8_t* psrc;
+                            int pcin, pcoff;
+                            if (cj < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = cj * CPC; }
+                            else { psrc = p.in2; pcin = p.Cin2; pcoff = (cj - p.nchunk1) * CPC; }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int id = nbr_s[(rbase + 16 * i) * KT + k2];
-                            if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
+                            for (int i = 0; i < 8; ++i) {
+                                const int id = nbr_s[(rbase + 16 * i) * KT + k2];
+                                if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
+                            }
                         }
                     }
                 } else if (TC_L2_PREFETCH && p.pf_mode == 1) {
@@ -783,6 +792,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 const long long slot = row0 + lane + 32 * h;
                 rowreg[h] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
             }
+            // mode 0 of the L2 prefetch: the rows of the first two offsets of this (upcoming) tile go to L2 now, a whole
+            // tile before their gather (the producers' own prefetch starts at the tile's third offset)
+            uint32_t first2 = 0u;
+            if (TC_L2_PREFETCH && p.pf_mode == 0 && KT > 1 && p.nbr) {
+                const uint32_t km = pair_mask(tp);
+                const uint32_t rest = km & (km - 1u);
+                first2 = km & ~(rest & (rest - 1u));  // the two lowest set bits
+            }
             int v[NJ];
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
@@ -793,6 +810,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 const int row = (rl >> 5) ? r1 : r0;
                 if (p.nbr) v[jj] = (row >= 0) ? __ldg(p.nbr + (long long)row * KT + k) : -1;
                 else v[jj] = row;
+                if (((first2 >> k) & 1u) && v[jj] >= 0) {
+                    for (int ch = 0; ch < p.nchunk1; ++ch)
+                        prefetch_l2(p.in1 + ((long long)v[jj] * p.Cin1 + ch * CPC) * ES);
+                    for (int ch = 0; ch < p.nchunk2; ++ch)
+                        prefetch_l2(p.in2 + ((long long)v[jj] * p.Cin2 + ch * CPC) * ES);
+                }
             }
             if (it >= 1) mbar_wait(bar_nbr_empty, (uint32_t)(it - 1) & 1u);
 #pragma unroll
@@ -1062,9 +1085,91 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 prof_[2] += (unsigned long long)(clock64() - t_epi0);
                 ++prof_[7];
 #endif
+            } else if (ES == 4) {
+                // fp32 rows of the tf32 mode, staged like the bf16 rows: 16-column sub-chunks (64 bytes per row), so
+                // residual loads and output stores are 64-byte row segments, 8 rows per warp access. B2ME_TF32: the
+                // stored values are rounded to tf32 (they feed the next tf32 MMA).
+                int crows[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) crows[m] = __shfl_sync(0xffffffffu, row, crow + 8 * m);
+                const float* resp = reinterpret_cast<const float*>(p.residual);
+                float* outp = reinterpret_cast<float*>(p.out);
+                mbar_wait(bar_tf, tf_par);
+                tc_fence_after();
+                if (n_my == 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
+                }
+                for (int ci = 0; ci < n_my; ++ci) {
+                    const int cb32 = chunk_col(ci);
+                    const int nsub = min(32, p.n_tile - cb32) >> 4;   // n_tile % 16 == 0: one or two 16-column sub-chunks
+                    for (int hs = 0; hs < nsub; ++hs) {
+                        const int cb = cb32 + 16 * hs;
+                        uint32_t r[16];
+                        tmem_ld_x16(tmem_col(cb), r);
+                        uint4 R[4];
+                        if (resp) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                R[m] = make_uint4(0u, 0u, 0u, 0u);
+                                if (crows[m] >= 0)
+                                    R[m] = __ldg(reinterpret_cast<const uint4*>(resp + (long long)crows[m] * p.Cout + n0 + cb +
+                                                                                cq * 4));
+                            }
+                        }
+                        tmem_ld_wait();
+                        if (hs == nsub - 1) release_after(ci);
+                        float v[16];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 sc = *reinterpret_cast<const float4*>(scale_s + n0 + cb + q4 * 4);
+                            const float4 sh = *reinterpret_cast<const float4*>(shift_s + n0 + cb + q4 * 4);
+                            v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                            v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                            v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                            v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
+                        }
+                        if (resp) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                const int rr = crow + 8 * m;
+                                st_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4), R[m]);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                const uint4 a = ld_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4));
+                                v[q4 * 4 + 0] += __uint_as_float(a.x);
+                                v[q4 * 4 + 1] += __uint_as_float(a.y);
+                                v[q4 * 4 + 2] += __uint_as_float(a.z);
+                                v[q4 * 4 + 3] += __uint_as_float(a.w);
+                            }
+                            __syncwarp();  // every lane has read its residual row before the buffer takes the outputs
+                        }
+                        tc_act_n(v, act_mode, p.slope);
+                        if (p.out_dtype == B2ME_TF32) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) v[q] = round_tf32(v[q]);
+                        }
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4),
+                                         make_uint4(__float_as_uint(v[q4 * 4]), __float_as_uint(v[q4 * 4 + 1]),
+                                                    __float_as_uint(v[q4 * 4 + 2]), __float_as_uint(v[q4 * 4 + 3])));
+                        __syncwarp();
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int rr = crow + 8 * m;
+                            const uint4 o = ld_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4));
+                            if (crows[m] >= 0)
+                                *reinterpret_cast<uint4*>(outp + (long long)crows[m] * p.Cout + n0 + cb + cq * 4) = o;
+                        }
+                        __syncwarp();  // staging is reused by the next sub-chunk
+                    }
+                }
             } else {
-                // fp32 rows (tf32 mode; bf16 parity tests): row-per-lane stores of 16-column chunks split between the
-                // two column halves. B2ME_TF32: the stored values are rounded to tf32 (they feed the next tf32 MMA).
+                // fp32 rows from bf16 operands (parity tests only): row-per-lane stores of 16-column chunks split
+                // between the two column halves.
                 mbar_wait(bar_tf, tf_par);
                 tc_fence_after();
                 const int n16 = p.n_tile >> 4;
@@ -1400,7 +1505,7 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
         head_bytes = (size_t)Cout * p.head_cp * 4;
     }
     // n_tile = 256 + 128 with bf16 rows out: early release of the 256-column part + alternating 128-column regions
-    p.rot128 = (!head && p.n_tile == 384 && TC_NSPLIT0 == 256 && out_dtype == B2ME_BF16 &&
+    p.rot128 = (!head && p.n_tile == 384 && TC_NSPLIT0 == 256 && (out_dtype == B2ME_BF16 || es == 4) &&
                 !(flags & B2ME_TC_FLAG_NO_ROT128)) ? 1 : 0;
     int cols = 32;
     while (cols < (p.rot128 ? 512 : p.acc_bufs * p.n_tile)) cols <<= 1;
@@ -1435,7 +1540,8 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     // the leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
     // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms), so it is an alternative the caller picks
     // per call; the parity tests run both.
-    p.pf_mode = (flags & B2ME_TC_FLAG_PF_NONE) ? 2 : ((flags & B2ME_TC_FLAG_PF_BULK) ? 1 : 0);
+    p.pf_mode = (flags & B2ME_TC_FLAG_PF_NONE) ? 2 : ((flags & B2ME_TC_FLAG_PF_BULK) ? 1 :
+                                                      ((flags & B2ME_TC_FLAG_PF_NEAR) ? 3 : 0));
     p.tma = 0;
     if ((flags & B2ME_TC_FLAG_TMA) && V_in > 0) {
         const uint64_t w_rows = (uint64_t)K * (p.nchunk1 + p.nchunk2) * (uint64_t)Cout;

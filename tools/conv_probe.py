@@ -30,8 +30,9 @@ def main():
     ap.add_argument("--path", default="cpasync", choices=["cpasync", "tma"], help="operand path (B2ME_TC_FLAG_TMA)")
     ap.add_argument("--no-rot128", action="store_true", help="384-column tiles: single accumulator (round-1 layout)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
-    ap.add_argument("--prefetch", default="chunk", choices=["chunk", "bulk", "none"], help="L2 prefetch of the next offset")
+    ap.add_argument("--prefetch", default="far", choices=["far", "near", "bulk", "none"], help="L2 prefetch scheme")
     ap.add_argument("--sb", type=int, default=0, help="B-ring stages override (flags bits 8-10; 0 = library default)")
+    ap.add_argument("--rounds", type=int, default=5, help="--sweep: interleaved timing rounds per variant")
     ap.add_argument("--sweep", action="store_true",
                     help="time every shape under a list of flag variants (operand path, prefetch mode, B-ring depth, "
                          "accumulator layout) on the same map: same-box A/B")
@@ -39,15 +40,16 @@ def main():
     a = ap.parse_args()
     import MinkowskiEngine as ME
     from MinkowskiEngine._lib import (lib, ptr, stream, check, BF16, TF32, TC_FLAG_TMA, TC_FLAG_NO_ROT128,
-                                      TC_FLAG_PF_BULK, TC_FLAG_PF_NONE)
+                                      TC_FLAG_PF_BULK, TC_FLAG_PF_NONE, TC_FLAG_PF_NEAR)
     op = TF32 if a.dtype == "tf32" else BF16
     flags = ((TC_FLAG_TMA if a.path == "tma" else 0) | (TC_FLAG_NO_ROT128 if a.no_rot128 else 0)
-             | {"chunk": 0, "bulk": TC_FLAG_PF_BULK, "none": TC_FLAG_PF_NONE}[a.prefetch] | ((a.sb & 7) << 8))
+             | {"far": 0, "near": TC_FLAG_PF_NEAR, "bulk": TC_FLAG_PF_BULK, "none": TC_FLAG_PF_NONE}[a.prefetch]
+             | ((a.sb & 7) << 8))
     variants = [("default", flags)]
     if a.sweep:
-        variants = [("default", 0), ("sb2", 2 << 8), ("sb4", 4 << 8), ("pf_bulk", TC_FLAG_PF_BULK),
-                    ("pf_none", TC_FLAG_PF_NONE), ("tma", TC_FLAG_TMA), ("tma+pf_bulk", TC_FLAG_TMA | TC_FLAG_PF_BULK),
-                    ("no_rot128", TC_FLAG_NO_ROT128), ("default_again", 0)]
+        variants = [("default", 0), ("pf_near", TC_FLAG_PF_NEAR), ("pf_none", TC_FLAG_PF_NONE), ("sb4", 4 << 8),
+                    ("tma", TC_FLAG_TMA), ("tma+pf_near", TC_FLAG_TMA | TC_FLAG_PF_NEAR),
+                    ("no_rot128", TC_FLAG_NO_ROT128)]
     adt = torch.float32 if a.dtype == "tf32" else torch.bfloat16
     from b200calib.synthetic import make_frame
     frames = [make_frame(13000 + i) for i in range(a.frames)]
@@ -102,24 +104,34 @@ def main():
                                          ptr(masks), K, V, cout, None, None, None, 1, 0.0, ptr(out), op, flags,
                                          stream()))
         if a.sweep:
+            # interleaved rounds (the SM clock drifts under the power cap): every variant is timed once per round, the
+            # reported time is the median over the rounds
             ref_out = None
-            for vname, vflags in variants:
-                flags = vflags
-                run()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(a.reps):
-                    run()
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / a.reps
-                cur = (logits if head else out).clone()
-                same = True if ref_out is None else bool(torch.equal(cur, ref_out))
-                ref_out = cur if ref_out is None else ref_out
-                print(f"K={K} {cin}->{cout} V={V} [{vname:14s}] {ms:8.3f} ms  {2.0 * pairs * cin * cout / ms / 1e9:7.0f} TFLOP/s"
-                      f"  bit-identical to the first variant: {same}", flush=True)
-                res.append(dict(K=K, Cin=cin, Cout=cout, V=V, variant=vname, ms=ms, same=same))
+            times = {vn: [] for vn, _ in variants}
+            same = {}
+            for rnd in range(a.rounds):
+                for vname, vflags in variants:
+                    flags = vflags
+                    if rnd == 0:
+                        run()
+                        torch.cuda.synchronize()
+                        cur = (logits if head else out).clone()
+                        same[vname] = True if ref_out is None else bool(torch.equal(cur, ref_out))
+                        ref_out = cur if ref_out is None else ref_out
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(a.reps):
+                        run()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    times[vname].append(e0.elapsed_time(e1) / a.reps)
+            for vname, _ in variants:
+                ms = float(np.median(times[vname]))
+                print(f"K={K} {cin}->{cout} V={V} [{vname:14s}] median {ms:8.3f} ms (min {min(times[vname]):.3f})  "
+                      f"{2.0 * pairs * cin * cout / ms / 1e9:7.0f} TFLOP/s  bit-identical to the first variant: {same[vname]}",
+                      flush=True)
+                res.append(dict(K=K, Cin=cin, Cout=cout, V=V, variant=vname, ms=ms, ms_min=min(times[vname]),
+                                same=same[vname]))
             continue
         run()
         torch.cuda.synchronize()

@@ -199,11 +199,11 @@ int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64_t V_out, i
 #define B2ME_TC_FLAG_NO_ROT128 2  /* 384-column tiles: one 384-column accumulator (round-1 layout) instead of the early
                                      release of the 256-column part + alternating 128-column regions; same results */
 
-#define B2ME_TC_FLAG_PF_BULK 4    /* L2 prefetch of the next offset's gathered rows by one cp.async.bulk.prefetch.L2 per row
-                                     instead of one prefetch.global.L2 per 128-byte chunk */
-#define B2ME_TC_FLAG_PF_NONE 8    /* no L2 prefetch (A/B) */
-#define B2ME_TC_FLAG_PF_NEAR 16   /* L2 prefetch of the NEXT offset only (default: two offsets ahead, and the first two
-                                     offsets of a tile a whole tile ahead) */
+#define B2ME_TC_FLAG_PF_BULK 4    /* L2 prefetch of the next offset's gathered rows by one cp.async.bulk.prefetch.L2 per row */
+#define B2ME_TC_FLAG_PF_NONE 8    /* no L2 prefetch: the default (kept so that callers can say so explicitly) */
+#define B2ME_TC_FLAG_PF_NEAR 16   /* L2 prefetch of the next offset's rows by one prefetch.global.L2 per 128-byte chunk (the
+                                     round-1 default; measured no faster than none) */
+/* bits 8-10: B-ring depth override (weight stages), 0 = library default (3) */
 
 /* V_in: rows of in1 (and of in2, which lies on the same coordinate map; with B2ME_TC_FLAG_TMA row indices outside
  * [0, V_in) read as zeros). op_dtype: type of in1 / in2 / packed_w (B2ME_BF16 | B2ME_TF32); residual rows are bf16

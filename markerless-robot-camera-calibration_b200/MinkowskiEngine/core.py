@@ -105,10 +105,9 @@ def set_tc_rot128(on):
 
 
 def set_tc_prefetch(mode):
-    """L2 prefetch of later kernel offsets' gathered rows in the tcgen05 convolution: "far" (default: one
-    prefetch.global.L2 per 128-byte chunk, two offsets ahead, the first two offsets of a tile a whole tile ahead),
-    "near" (the next offset only), "bulk" (one cp.async.bulk.prefetch.L2 per row of the next offset) or "none"."""
-    bits = {"far": 0, "near": _lib.TC_FLAG_PF_NEAR, "bulk": _lib.TC_FLAG_PF_BULK, "none": _lib.TC_FLAG_PF_NONE}[mode]
+    """L2 prefetch of the next kernel offset's gathered rows in the tcgen05 convolution: "none" (default), "near"
+    (one prefetch.global.L2 per 128-byte chunk) or "bulk" (one cp.async.bulk.prefetch.L2 per row)."""
+    bits = {"none": 0, "near": _lib.TC_FLAG_PF_NEAR, "bulk": _lib.TC_FLAG_PF_BULK}[mode]
     _State.tc_flags = (_State.tc_flags & ~(_lib.TC_FLAG_PF_BULK | _lib.TC_FLAG_PF_NONE | _lib.TC_FLAG_PF_NEAR)) | bits
 
 

@@ -108,9 +108,8 @@ struct TcParams {
     int n_pairs;  // 256-row tile pairs
     int debug;    // debug build only (B2ME_TC_DEBUG): 1 skip the A gathers, 2 skip the B copies, 4 skip the MMAs
     int tma;      // 1: operands come through the TMA unit (gather4 rows / 2-D weight boxes, cta_group::2)
-    int pf_mode;  // L2 prefetch of later offsets' rows: 0 prefetch.global.L2 per 128-byte chunk two offsets ahead + the
-                  // first two offsets of a tile by the kernel-map warps, 1 one cp.async.bulk.prefetch.L2 per row of the
-                  // next offset, 2 none, 3 per chunk for the next offset only (round-1 scheme)
+    int pf_mode;  // L2 prefetch of the next offset's rows: 2 none (default), 0 prefetch.global.L2 per 128-byte chunk
+                  // (round-1 scheme), 1 one cp.async.bulk.prefetch.L2 per row
     // tensor maps (TMA mode): the two sources as [V_in, Cin] with a (128-byte chunk) x 1-row box (SWIZZLE_128B; rows are
     // picked by tile::gather4, absent neighbours (-1) and channels past Cin are out of bounds = zero-filled) and the
     // packed weights as 128-byte rows (box = one CTA's half of an item, no swizzle: the image is pre-swizzled)
@@ -379,11 +378,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
 
-    // carve: [A ring S x 16 KB][B ring SB x b_bytes][nbr_s 128*KT i32][scale Cout][shift Cout][head W2 Cout*head_cp][epilogue staging 8 x 2 KB]
+    // carve: [A ring S x 16 KB][B ring SB x b_bytes][nbr_s 2 x 128*KT i32][scale Cout][shift Cout][head W2 Cout*head_cp][epilogue staging 8 x 2 KB]
     //        [barriers][tmem ptr]
     uint32_t off = (uint32_t)S * TC_A_BYTES + (uint32_t)SB * p.b_bytes;
-    int32_t* nbr_s = reinterpret_cast<int32_t*>(sm + off);
-    off += TC_BM * KT * 4;
+    // kernel-map rows of the tile being gathered and of the next one (double buffer: the prefetch warps publish tile
+    // t + 1 while the producers still read tile t, so the producers never wait for the hand-over)
+    int32_t* nbr_s0 = reinterpret_cast<int32_t*>(sm + off);
+    off += 2 * TC_BM * KT * 4;
     off = (off + 15u) & ~15u;
     float* scale_s = reinterpret_cast<float*>(sm + off);
     off += p.Cout * 4;
@@ -399,10 +400,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     off += 8 * TC_MAX_STAGES;
     const uint32_t bar_empty = base + off;
     off += 8 * TC_MAX_STAGES;
-    const uint32_t bar_nbr_full = base + off;
-    off += 8;
-    const uint32_t bar_nbr_empty = base + off;
-    off += 8;
+    const uint32_t bar_nbr_full = base + off;   // [2]
+    off += 16;
+    const uint32_t bar_nbr_empty = base + off;  // [2]
+    off += 16;
     const uint32_t bar_tmem_full = base + off;   // [2] one per accumulator buffer
     off += 16;
     const uint32_t bar_tmem_empty = base + off;  // [3] accumulator buffers / (256-column part, 128-column regions 0, 1)
@@ -417,8 +418,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             mbar_init(bar_full + 8 * s, p.tma ? 1 : (rank == 0 ? 130 : 129));
             mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit (multicast from the leader)
         }
-        mbar_init(bar_nbr_full, 2);            // 2 prefetch warps
-        mbar_init(bar_nbr_empty, 4);           // 4 producer warps
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_nbr_full + 8 * b, 2);   // 2 prefetch warps
+            mbar_init(bar_nbr_empty + 8 * b, 4);  // 4 producer warps
+        }
         for (int b = 0; b < 2; ++b) mbar_init(bar_tmem_full + 8 * b, 1);  // tcgen05.commit (multicast from the leader)
         for (int b = 0; b < 3; ++b)
             mbar_init(bar_tmem_empty + 8 * b, 2 * TC_EPI_WARPS);  // epilogue warps of both CTAs (leader's barrier)
@@ -470,7 +473,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             const uint32_t kmask = kmask_next;
             const int tpn = item_pair(it + 1);
             if (tpn < p.n_pairs) kmask_next = __shfl_sync(0xffffffffu, pair_mask(tpn), 0);
-            mbar_wait(bar_nbr_full, (uint32_t)it & 1u);
+            const int32_t* nbr_s = nbr_s0 + (it & 1) * (TC_BM * KT);
+            mbar_wait(bar_nbr_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
 #pragma unroll 1
             for (uint32_t m = kmask; m; m &= m - 1u) {
                 const int k = __ffs((int)m) - 1;
@@ -480,13 +484,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 for (int q = 0; q < 32; ++q) ids[q] = __shfl_sync(0xffffffffu, id, q);
                 if ((m & (m - 1u)) == 0u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_nbr_empty);
+                    if (lane == 0) mbar_arrive(bar_nbr_empty + 8 * (it & 1));
                 } else if (TC_L2_PREFETCH && p.pf_mode != 2) {
-                    // pull the rows of a later offset into L2 (mode 0: two offsets ahead, see the cp.async producers)
-                    uint32_t m2 = m & (m - 1u);
-                    if (p.pf_mode == 0) m2 &= m2 - 1u;
-                    const int k2 = m2 ? __ffs((int)m2) - 1 : 0;
-                    const int id2 = m2 ? nbr_s[(32 * warp + lane) * KT + k2] : -1;
+                    // optional: pull the rows of the NEXT offset into L2 (see the cp.async producers)
+                    const uint32_t m2 = m & (m - 1u);
+                    const int k2 = __ffs((int)m2) - 1;
+                    const int id2 = nbr_s[(32 * warp + lane) * KT + k2];
                     if (id2 >= 0) {
                         if (p.pf_mode == 1) {
                             prefetch_l2_bulk(p.in1 + (long long)id2 * p.Cin1 * ES, (uint32_t)(p.Cin1 * ES));
@@ -530,7 +533,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
             const uint32_t kmask = kmask_next;
             const int tpn = item_pair(it + 1);
             if (tpn < p.n_pairs) kmask_next = pair_mask(tpn);
-            PROF(1, mbar_wait(bar_nbr_full, (uint32_t)it & 1u));
+            const int32_t* nbr_s = nbr_s0 + (it & 1) * (TC_BM * KT);
+            PROF(1, mbar_wait(bar_nbr_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u));
 #pragma unroll 1
             for (int k = 0; k < KT; ++k) {
                 if (!((kmask >> k) & 1u)) continue;
@@ -539,28 +543,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 for (int i = 0; i < 8; ++i) idx[i] = nbr_s[(rbase + 16 * i) * KT + k];
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_nbr_empty);
-                } else if (TC_L2_PREFETCH && (p.pf_mode == 0 || p.pf_mode == 3)) {
-                    // the gathered rows come from all over the tensor (DRAM latency, and its tail: a stage is full only
-                    // when the slowest of its 256 rows has landed, >> the ring's depth in time): pull the rows of a
-                    // LATER offset into L2 now. Mode 0: the offset after the next one (two offsets = 2 nchunk items
-                    // ahead; the first two offsets of a tile are prefetched by the kernel-map warps a whole tile
-                    // ahead), mode 3: the next offset (round-1 scheme).
-                    // lane j takes the 128-byte chunks j, j + 8, ... of each of this thread's 8 rows.
-                    uint32_t later = kmask >> (k + 1);                 // offsets after k (non-zero here)
-                    if (p.pf_mode == 0) later &= later - 1u;           // drop the next one
-                    if (later != 0u) {
-                        const int k2 = k + 1 + __ffs((int)later) - 1;
-                        for (int cj = j; cj < nchunk; cj += 8) {
-                            const uint8_t* psrc;
-                            int pcin, pcoff;
-                            if (cj < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = cj * CPC; }
-                            else { psrc = p.in2; pcin = p.Cin2; pcoff = (cj - p.nchunk1) * CPC; }
+                    if (lane == 0) mbar_arrive(bar_nbr_empty + 8 * (it & 1));
+                } else if (TC_L2_PREFETCH && p.pf_mode == 0) {
+                    // optional (B2ME_TC_FLAG_PF_NEAR): pull the rows of the NEXT offset into L2 now, one whole offset
+                    // (= nchunk items) ahead of their gather. lane j takes the 128-byte chunks j, j + 8, ... of each of
+                    // this thread's 8 rows. Measured (interleaved A/B, same box): no gain over no prefetch at all
+                    // (10.6 vs 10.4 ms at tensor stride 1, 5.54 vs 5.27 ms at stride 2), so it is off by default.
+                    const int k2 = k + 1 + __ffs((int)(kmask >> (k + 1))) - 1;
+                    for (int cj = j; cj < nchunk; cj += 8) {
+                        const uint8_t* psrc;
+                        int pcin, pcoff;
+                        if (cj < p.nchunk1) { psrc = p.in1; pcin = p.Cin1; pcoff = cj * CPC; }
+                        else { psrc = p.in2; pcin = p.Cin2; pcoff = (cj - p.nchunk1) * CPC; }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int id = nbr_s[(rbase + 16 * i) * KT + k2];
-                                if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
-                            }
+                        for (int i = 0; i < 8; ++i) {
+                            const int id = nbr_s[(rbase + 16 * i) * KT + k2];
+                            if (id >= 0) prefetch_l2(psrc + ((long long)id * pcin + pcoff) * ES);
                         }
                     }
                 } else if (TC_L2_PREFETCH && p.pf_mode == 1) {
@@ -792,14 +790,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 const long long slot = row0 + lane + 32 * h;
                 rowreg[h] = (slot < p.V_out) ? (p.perm ? __ldg(p.perm + slot) : (int)slot) : -1;
             }
-            // mode 0 of the L2 prefetch: the rows of the first two offsets of this (upcoming) tile go to L2 now, a whole
-            // tile before their gather (the producers' own prefetch starts at the tile's third offset)
-            uint32_t first2 = 0u;
-            if (TC_L2_PREFETCH && p.pf_mode == 0 && KT > 1 && p.nbr) {
-                const uint32_t km = pair_mask(tp);
-                const uint32_t rest = km & (km - 1u);
-                first2 = km & ~(rest & (rest - 1u));  // the two lowest set bits
-            }
             int v[NJ];
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) {
@@ -810,18 +800,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 const int row = (rl >> 5) ? r1 : r0;
                 if (p.nbr) v[jj] = (row >= 0) ? __ldg(p.nbr + (long long)row * KT + k) : -1;
                 else v[jj] = row;
-                if (((first2 >> k) & 1u) && v[jj] >= 0) {
-                    for (int ch = 0; ch < p.nchunk1; ++ch)
-                        prefetch_l2(p.in1 + ((long long)v[jj] * p.Cin1 + ch * CPC) * ES);
-                    for (int ch = 0; ch < p.nchunk2; ++ch)
-                        prefetch_l2(p.in2 + ((long long)v[jj] * p.Cin2 + ch * CPC) * ES);
-                }
             }
-            if (it >= 1) mbar_wait(bar_nbr_empty, (uint32_t)(it - 1) & 1u);
+            int32_t* nbr_s = nbr_s0 + (it & 1) * (TC_BM * KT);
+            if (it >= 2) mbar_wait(bar_nbr_empty + 8 * (it & 1), (uint32_t)((it >> 1) - 1) & 1u);
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) nbr_s[64 * wl * KT + lane + 32 * jj] = v[jj];
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_nbr_full);
+            if (lane == 0) mbar_arrive(bar_nbr_full + 8 * (it & 1));
         }
     } else {
         // =============================== epilogue ===============================
@@ -1514,8 +1499,8 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     if (pairs * p.n_ntiles > 0x7fffffff) return B2ME_EUNSUPPORTED;
     p.n_pairs = (int)pairs;
 
-    const size_t fixed = 1024 /*align slack*/ + (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 + head_bytes + 16 +
-                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 16 + 16 + 24 + 16;
+    const size_t fixed = 1024 /*align slack*/ + 2 * (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 + head_bytes + 16 +
+                         (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 32 + 16 + 24 + 16;
     // B ring: 3 stages of weights (L2-resident, short latency; A/B override in flags bits 8-10), A ring: as many
     // 16 KB stages of gathered rows (DRAM, long latency) as the rest of shared memory holds
     int SB = (flags >> 8) & 7;
@@ -1540,8 +1525,7 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     // the leader's barrier, no relay, no proxy fence). Measured on the same box it runs at the speed of the default
     // cp.async gather + bulk copy + relay path (K27 384->384: 5.02 vs 5.04 ms), so it is an alternative the caller picks
     // per call; the parity tests run both.
-    p.pf_mode = (flags & B2ME_TC_FLAG_PF_NONE) ? 2 : ((flags & B2ME_TC_FLAG_PF_BULK) ? 1 :
-                                                      ((flags & B2ME_TC_FLAG_PF_NEAR) ? 3 : 0));
+    p.pf_mode = (flags & B2ME_TC_FLAG_PF_BULK) ? 1 : ((flags & B2ME_TC_FLAG_PF_NEAR) ? 0 : 2);
     p.tma = 0;
     if ((flags & B2ME_TC_FLAG_TMA) && V_in > 0) {
         const uint64_t w_rows = (uint64_t)K * (p.nchunk1 + p.nchunk2) * (uint64_t)Cout;

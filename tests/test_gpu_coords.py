@@ -1,4 +1,5 @@
-"""K1-K3 parity (bit-exact): voxel coordinates, inverse maps, voxel features, stride maps, kernel maps."""
+"""K1-K3 parity: voxel coordinates, inverse maps, stride maps, kernel maps bit-exact; UNWEIGHTED_AVERAGE voxel
+features equal to the oracle's order-independent fixed-point definition and within 1 ulp of the float64 mean."""
 import numpy as np
 import pytest
 import torch
@@ -31,8 +32,20 @@ def test_voxelize_bit_exact(n, scale, batches):
     os_, cs = of.sparse(), cf.sparse()
     assert torch.equal(cs.C.cpu(), os_.C)                                   # coordinates, first-occurrence order
     assert torch.equal(cf.inverse_mapping.cpu().long(), of.inverse_mapping)  # inverse map
-    assert torch.equal(cs.F.cpu(), os_.F)                                   # fixed-point mean: bit-exact features
+    # voxel mean: the kernel's order-independent 2^32 fixed-point sum, which the oracle restates (so this equality is
+    # agreement with that definition, not with ME's float arithmetic) ...
+    assert torch.equal(cs.F.cpu(), os_.F)
     assert torch.equal(cs.slice(cf).F.cpu(), os_.slice(of).F)
+    # ... and, independently, within 1 ulp of the float64 mean of the member points rounded to fp32
+    inv = of.inverse_mapping.numpy()
+    fe = np.concatenate(feats).astype(np.float64)
+    V = os_.F.shape[0]
+    sums = np.zeros((V, fe.shape[1]))
+    np.add.at(sums, inv, fe)
+    mean64 = sums / np.bincount(inv, minlength=V)[:, None]
+    got = cs.F.cpu().numpy()
+    ulp = np.spacing(np.abs(mean64).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(got.astype(np.float64) - mean64) <= ulp), "voxel mean further than 1 ulp from the fp64 mean"
 
 
 def test_voxelize_edge_cases():

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--path", default="cpasync", choices=["cpasync", "tma"], help="operand path (B2ME_TC_FLAG_TMA)")
     ap.add_argument("--no-rot128", action="store_true", help="384-column tiles: single accumulator (round-1 layout)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
-    ap.add_argument("--prefetch", default="far", choices=["far", "near", "bulk", "none"], help="L2 prefetch scheme")
+    ap.add_argument("--prefetch", default="none", choices=["none", "near", "bulk"], help="L2 prefetch scheme")
     ap.add_argument("--sb", type=int, default=0, help="B-ring stages override (flags bits 8-10; 0 = library default)")
     ap.add_argument("--rounds", type=int, default=5, help="--sweep: interleaved timing rounds per variant")
     ap.add_argument("--sweep", action="store_true",
@@ -43,12 +43,11 @@ def main():
                                       TC_FLAG_PF_BULK, TC_FLAG_PF_NONE, TC_FLAG_PF_NEAR)
     op = TF32 if a.dtype == "tf32" else BF16
     flags = ((TC_FLAG_TMA if a.path == "tma" else 0) | (TC_FLAG_NO_ROT128 if a.no_rot128 else 0)
-             | {"far": 0, "near": TC_FLAG_PF_NEAR, "bulk": TC_FLAG_PF_BULK, "none": TC_FLAG_PF_NONE}[a.prefetch]
+             | {"near": TC_FLAG_PF_NEAR, "bulk": TC_FLAG_PF_BULK, "none": TC_FLAG_PF_NONE}[a.prefetch]
              | ((a.sb & 7) << 8))
     variants = [("default", flags)]
     if a.sweep:
-        variants = [("default", 0), ("pf_near", TC_FLAG_PF_NEAR), ("pf_none", TC_FLAG_PF_NONE), ("sb4", 4 << 8),
-                    ("tma", TC_FLAG_TMA), ("tma+pf_near", TC_FLAG_TMA | TC_FLAG_PF_NEAR),
+        variants = [("default", 0), ("pf_near", TC_FLAG_PF_NEAR), ("sb2", 2 << 8), ("sb4", 4 << 8), ("tma", TC_FLAG_TMA),
                     ("no_rot128", TC_FLAG_NO_ROT128)]
     adt = torch.float32 if a.dtype == "tf32" else torch.bfloat16
     from b200calib.synthetic import make_frame

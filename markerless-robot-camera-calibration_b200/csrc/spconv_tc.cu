@@ -336,14 +336,14 @@ __device__ __forceinline__ void tc_act_n(float (&v)[N], int mode, float slope) {
     }
 }
 
-// fused head: acc[c] += x[q] * W2[col0 + q][c] for the 32 columns of one accumulator chunk; W2 rows of HCP floats in
+// fused head: acc[c] += x[q] * W2[col0 + q][c] for the 16 columns of one accumulator sub-chunk; W2 rows of HCP floats in
 // shared memory (every lane reads the same address: broadcast)
 template <int HC, int NH>
-__device__ __forceinline__ void tc_head_accumulate(const float (&x)[32], const float* __restrict__ w_rows, int hcp,
+__device__ __forceinline__ void tc_head_accumulate(const float (&x)[16], const float* __restrict__ w_rows, int hcp,
                                                    float (&hacc)[NH]) {
     static_assert(HC <= NH, "head accumulators");
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+    for (int q = 0; q < 16; ++q) {
         float w[(HC + 3) / 4 * 4];
 #pragma unroll
         for (int g = 0; g < (HC + 3) / 4; ++g) {
@@ -886,15 +886,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
-                for (int ci = 0; ci < n_my; ++ci) {
-                    const int cb = chunk_col(ci);
-                    uint32_t r[32];
-                    tmem_ld_x32(tmem_col(cb), r);  // head mode: n_tile % 64 == 0, every chunk is 32 columns wide
+                // 16-column sub-chunks with two register sets: the tcgen05.ld of sub-chunk i + 1 is in flight while
+                // sub-chunk i is processed (a TMEM read under the MMAs' own TMEM traffic costs about as much as the
+                // arithmetic on it); head mode: n_tile % 64 == 0, every 32-column chunk is two full sub-chunks
+                const int n_sub = 2 * n_my;
+                auto sub_col = [&](int si) -> int { return chunk_col(si >> 1) + 16 * (si & 1); };
+                uint32_t ra[16], rb[16];
+                if (n_sub > 0) tmem_ld_x16(tmem_col(sub_col(0)), ra);
+                for (int si = 0; si < n_sub; ++si) {
+                    const int cb = sub_col(si);
                     tmem_ld_wait();
-                    release_after(ci);
-                    float x[32];
+                    uint32_t r[16];
+                    if (si & 1) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
+                        for (int q = 0; q < 16; ++q) r[q] = rb[q];
+                        if (si + 1 < n_sub) tmem_ld_x16(tmem_col(sub_col(si + 1)), ra);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) r[q] = ra[q];
+                        if (si + 1 < n_sub) tmem_ld_x16(tmem_col(sub_col(si + 1)), rb);
+                    }
+                    if (si == n_sub - 1) release_after(n_my - 1);
+                    float x[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
                         const int col = n0 + cb + q4 * 4;
                         const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
                         const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
@@ -907,7 +922,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     // the hidden activation is a bf16 (tf32-rounded fp32) tensor in the unfused data path: same rounding
                     if (ES == 2) {
 #pragma unroll
-                        for (int q = 0; q < 32; q += 2) {
+                        for (int q = 0; q < 16; q += 2) {
                             __nv_bfloat162 h = __floats2bfloat162_rn(x[q], x[q + 1]);
                             const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
                             x[q] = __uint_as_float(u << 16);
@@ -915,7 +930,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) x[q] = round_tf32(x[q]);
+                        for (int q = 0; q < 16; ++q) x[q] = round_tf32(x[q]);
                     }
                     const float* w_rows = head_w_s + (n0 + cb) * p.head_cp;
                     switch (p.head_c) {   // exact FMA count for the class counts of the reference's heads
@@ -1504,7 +1519,7 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     // B ring: 3 stages of weights (L2-resident, short latency; A/B override in flags bits 8-10), A ring: as many
     // 16 KB stages of gathered rows (DRAM, long latency) as the rest of shared memory holds
     int SB = (flags >> 8) & 7;
-    if (SB == 0) SB = 3;
+    if (SB == 0) SB = K == 27 ? 3 : 4;   // measured (interleaved A/B): K = 8 384->384 1.55 vs 1.71 ms with 4 vs 3 stages
     if (SB < 2) SB = 2;
     int S = TC_MAX_STAGES;
     while (S >= 2 && fixed + (size_t)S * TC_A_BYTES + (size_t)(SB < S ? SB : S) * p.b_bytes > TC_MAX_SMEM) --S;

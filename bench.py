@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--strong-frames", type=int, default=0,
                     help="strong scaling: this many frames IN TOTAL with uneven point counts, sharded over the ranks by "
                          "greedy balancing; gather + calibrate inside the timed region")
+    ap.add_argument("--vote", action="store_true",
+                    help="also run the vote head (RobotNetVote + get_pred_center, model/robotnet_vote.py, utils/output.py:"
+                         "45-64) on the EE crops inside every step; InferenceEngine.predict does not call it, so it is off "
+                         "in the headline workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--stages", action="store_true", help="one extra (untimed) step with synchronised per-stage times")
@@ -316,7 +320,13 @@ class Workbench:
         from b200calib.synthetic import ee_surface_cloud
         self.cad = torch.from_numpy(ee_surface_cloud(4096, SEED)).to(self.dev)
         self.cfg = PipelineConfig(seg_scale=args.scale, icp_enabled=not args.no_icp)
-        self.eng = BatchedInferenceEngine(self.seg, self.rot, self.kp, cad_points=self.cad, config=self.cfg)
+        vote = None
+        if getattr(args, "vote", False):
+            from b200calib.models import make_models, randomize_bn_stats
+            torch.manual_seed(SEED + 3)
+            vote = randomize_bn_stats(make_models(ME).RobotNetVote(3, num_classes=2), SEED + 3).eval().to(self.dev)
+        self.eng = BatchedInferenceEngine(self.seg, self.rot, self.kp, cad_points=self.cad, config=self.cfg,
+                                          vote_model=vote)
         self.frames = frames
         self.pack_xyzrgb = pack_xyzrgb
 
@@ -970,7 +980,12 @@ def run_strong(args, rank, world, local):
                 r.key_points_base_pose = (get_base2cam_pose(r.key_points_pose, ee2base)
                                           if r.key_points_pose is not None else None)
                 data.setdefault(int(row[0]) % 5, []).append(r)
-            cal = calibrate(data) if data else None
+            try:
+                cal = calibrate(data) if data else None
+            except ValueError:
+                # the reference's calibrate (app/inference_engine.py:152-194) stacks base_pose with key_points_base_pose
+                # and raises exactly like this when no frame of a position has a key-point pose (random-init weights)
+                cal = None
         return allrec, cal
 
     for _ in range(max(1, args.warmup)):

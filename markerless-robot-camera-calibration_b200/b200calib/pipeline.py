@@ -52,6 +52,7 @@ class PipelineConfig:
     # device for every posed frame (b2me_sanity_check). Off: no frame is ever marked confident, so the calibration tail
     # (calibration.calibrate_individual filters on is_confident) cannot silently average unchecked frames.
     sanity_check: bool = True
+    vote_ee_r: float = 0.02               # PARAM.ee_r (config/default.yaml:8): offset of the voted centre along -x of the EE
     sanity_min_ee_points: int = 2048      # INFERENCE.SANITY.min_num_of_ee_points
     sanity_kp_error_margin: float = 0.05  # INFERENCE.KEY_POINTS.error_margin
 
@@ -67,6 +68,7 @@ class FrameResult:
     key_points_base_pose: Optional[np.ndarray] = None
     is_confident: bool = False
     icp_stats: Optional[np.ndarray] = None
+    vote_center: Optional[np.ndarray] = None   # get_pred_center of the vote head (utils/output.py:45-64), when it runs
 
 
 def normalize_colors_(rgb, bidx=None, offs=None):
@@ -166,7 +168,8 @@ class BatchedInferenceEngine:
     stage_times = None  # dict name -> ms when enabled
 
     def __init__(self, seg_model, rot_model=None, kp_model=None, cad_points=None, config=None,
-                 reference_key_points=REFERENCE_KEY_POINTS):
+                 reference_key_points=REFERENCE_KEY_POINTS, vote_model=None):
+        self.vote_model = vote_model.eval() if vote_model is not None else None   # RobotNetVote (model/robotnet_vote.py)
         self.seg_model = seg_model.eval()
         self.rot_model = rot_model.eval() if rot_model is not None else None
         self.kp_model = kp_model.eval() if kp_model is not None else None
@@ -268,6 +271,22 @@ class BatchedInferenceEngine:
             pos = out_utils.translation_magic_batched(pts, soffs, quat, cfg.translation_x_offset)
             ee_pose = torch.cat((pos, quat.double()), dim=1)  # x,y,z,qw,qx,qy,qz
 
+        # --- vote head (model/robotnet_vote.py:36-71 + utils/output.py:45-64, the path of test_vote.py:75-101): per-point
+        #     logits of RobotNetVote on the crop, mean coordinate of the 8 points with the largest "centre" logit, moved
+        #     by R(q) [-ee_r, 0, 0] with the rotation network's quaternion. Optional: InferenceEngine.predict does not
+        #     call it.
+        vote_center = None
+        if self.vote_model is not None:
+            with _Stage(self, "vote"):
+                vfld = _field(rot_pts, feats, segf, cfg.rot_scale, S)
+                vout = self.vote_model(vfld.sparse()).slice(vfld).F.float().contiguous()
+                ctr = out_utils.vote_centers_batched(vout, pts, soffs, col=1, topk=8)          # [S,3] f32
+                off = torch.tensor([-cfg.vote_ee_r, 0.0, 0.0], dtype=torch.float32, device=dev)
+                qn = quat / quat.norm(dim=1, keepdim=True)
+                Rq = _poses_to_matrices(torch.cat((torch.zeros((S, 3), dtype=torch.float64, device=dev), qn.double()),
+                                                  dim=1))[:, :3, :3].float()
+                vote_center = ctr + (Rq @ off)
+
         # --- key points (app/inference_engine.py:491-559) + Kabsch (:384-393)
         kp_T = None
         bp = kp_xyz = None
@@ -327,7 +346,9 @@ class BatchedInferenceEngine:
         with _Stage(self, "readback"):
             conf_col = (confident.double() if confident is not None
                         else torch.zeros((S,), dtype=torch.float64, device=dev)).unsqueeze(1)
-            pack = [ee_T.reshape(S, 16), ee_pose, conf_col]   # ee_pose: before the ICP refinement
+            vote_col = (vote_center.double() if vote_center is not None
+                        else torch.full((S, 3), float("nan"), dtype=torch.float64, device=dev))
+            pack = [ee_T.reshape(S, 16), ee_pose, conf_col, vote_col]   # ee_pose: before the ICP refinement
             if stats is not None:
                 pack.append(stats)
             if kp_T is not None:
@@ -337,10 +358,11 @@ class BatchedInferenceEngine:
                     pack.append(kstats)
                 pack.append(kp_T0.reshape(S, 16))
             host = torch.cat(pack, dim=1).cpu().numpy()
-            c = 24
+            c = 27
             res["ee_T"] = host[:, :16].reshape(S, 4, 4)
             res["ee_pose_initial"] = host[:, 16:23]
             res["confident"] = host[:, 23] > 0.5
+            res["vote_center"] = host[:, 24:27] if vote_center is not None else None
             res["kp_threshold"] = th
             if stats is not None:
                 res["icp_stats"] = host[:, c:c + 4]
@@ -540,6 +562,8 @@ class BatchedInferenceEngine:
                 r.key_points_pose = pose["kp_pose"][j]
             if pose.get("icp_stats") is not None:
                 r.icp_stats = pose["icp_stats"][j]
+            if pose.get("vote_center") is not None:
+                r.vote_center = pose["vote_center"][j]
             if ee2base_poses is not None and ee2base_poses[f] is not None:
                 if r.ee_pose is not None:
                     r.base_pose = get_base2cam_pose(r.ee_pose, ee2base_poses[f])

@@ -1014,17 +1014,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
+                // 16-column halves with two register sets: while one half of a chunk is scaled / activated / packed, the
+                // tcgen05.ld of the next half (or of the next chunk's first half) is in flight
+                uint32_t ra[16], rb[16];
+                if (n_my > 0) tmem_ld_x16(tmem_col(chunk_col(0)), ra);
                 for (int ci = 0; ci < n_my; ++ci) {
                     const int cb = chunk_col(ci);
-                    const int cw = min(32, p.n_tile - cb);
-                    uint32_t r[32];
-                    if (cw == 32) {
-                        tmem_ld_x32(tmem_col(cb), r);
-                    } else {
-                        tmem_ld_x16(tmem_col(cb), r);
-#pragma unroll
-                        for (int q = 16; q < 32; ++q) r[q] = 0u;
-                    }
+                    const int cw = min(32, p.n_tile - cb);   // 32, or 16 for the last chunk of a tile with n_tile % 32 == 16
                     if (resp) {
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
@@ -1034,42 +1030,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         __syncwarp();
                         if (ci + 1 < n_my) load_res(chunk_col(ci + 1));  // in flight during this chunk's math and stores
                     }
-                    tmem_ld_wait();
-                    release_after(ci);  // this warp's part of the accumulator (region) is read: release it
-                    float v[32];
 #pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
-                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
-                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
-                        v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
-                        v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
-                        v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
-                        v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
-                    }
-                    if (resp) {
+                    for (int half = 0; half < 2; ++half) {
+                        if (half == 1 && cw == 16) break;
+                        tmem_ld_wait();
+                        uint32_t r[16];
+                        if (half == 0) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) r[q] = ra[q];
+                            if (cw == 32) tmem_ld_x16(tmem_col(cb + 16), rb);
+                            else if (ci + 1 < n_my) tmem_ld_x16(tmem_col(chunk_col(ci + 1)), ra);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) r[q] = rb[q];
+                            if (ci + 1 < n_my) tmem_ld_x16(tmem_col(chunk_col(ci + 1)), ra);
+                        }
+                        if (half == 1 || cw == 16) release_after(ci);  // all columns of chunk ci are in registers
+                        float v[16];
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4) {
-                            const uint4 a = ld_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4));
-                            const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+                            const int col = min(n0 + cb + 16 * half + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
+                            const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
+                            const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                            v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                            v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                            v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                            v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
+                        }
+                        if (resp) {   // this lane's own row of the staged residual block: pieces 2 half, 2 half + 1
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
-                                v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+                            for (int q4 = 0; q4 < 2; ++q4) {
+                                const uint4 a4 = ld_shared_v4(own + (uint32_t)(((2 * half + q4) ^ own_sw) << 4));
+                                const uint32_t wv[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
+                                    v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+                                }
                             }
                         }
-                        __syncwarp();  // every lane has read its residual row before the buffer takes the outputs
-                    }
-                    tc_act_n(v, act_mode, p.slope);
+                        tc_act_n(v, act_mode, p.slope);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint32_t wv[4];
+                        for (int q4 = 0; q4 < 2; ++q4) {
+                            uint32_t wv[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(v[q4 * 8 + 2 * e], v[q4 * 8 + 2 * e + 1]);
-                            wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                            for (int e = 0; e < 4; ++e) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(v[q4 * 8 + 2 * e], v[q4 * 8 + 2 * e + 1]);
+                                wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            // the lane overwrites the residual pieces it has just read (its own row only)
+                            st_shared_v4(own + (uint32_t)(((2 * half + q4) ^ own_sw) << 4),
+                                         make_uint4(wv[0], wv[1], wv[2], wv[3]));
                         }
-                        st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
                     }
                     __syncwarp();
 #pragma unroll

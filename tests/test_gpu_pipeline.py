@@ -287,3 +287,40 @@ def test_predict_stream_matches_sequential(setup):
                 assert np.array_equal(p0["kp_T"], p1["kp_T"], equal_nan=True)
     finally:
         ME.set_compute_dtype(torch.float32)
+
+
+def test_vote_stage_matches_oracle(setup):
+    """optional vote stage of the batched engine (RobotNetVote on the EE crops + get_pred_center, the path of the
+    reference's test_vote.py:75-101) against the oracle: the unchanged topology on the oracle package per crop, then
+    utils/output.py:45-64 as restated (and golden-pinned) in oracle/geometry.py::pred_center. fp32 networks."""
+    ME, o, c, frames = setup
+    from b200calib.pipeline import BatchedInferenceEngine, PipelineConfig
+    torch.manual_seed(21)
+    MO, MC = make_models(OME), make_models(ME)
+    ov = randomize_bn_stats(MO.RobotNetVote(3, num_classes=2, variant=VARIANT)).eval()
+    cv = MC.RobotNetVote(3, num_classes=2, variant=VARIANT)
+    cv.load_state_dict(ov.state_dict())
+    cfgd = dict(seg_scale=100.0, rot_scale=200.0, kp_scale=400.0, ee_point_counts_threshold=128, kp_conf_threshold=0.0)
+    eng = BatchedInferenceEngine(c["seg"], c["rot"], None, cad_points=None, vote_model=cv.cuda().eval(),
+                                 config=PipelineConfig(icp_enabled=False, sanity_check=False, **cfgd))
+    ME.set_compute_dtype(torch.float32)
+    res = eng.predict_batch([(f["points"], f["rgb"]) for f in frames], gt_labels=[f["labels"] for f in frames])
+    seen = 0
+    for f, r in zip(frames, res):
+        if r.ee_pose is None:
+            continue
+        seg = OP.filter_ee(f["points"], f["labels"])
+        ee = f["points"][seg == 2]
+        rgbn = OP.normalize_colors(f["rgb"])[seg == 2]
+        cpts = OP.center_at_origin(ee)[0]
+        with torch.no_grad():
+            q = o["rot"](OP._field(cpts, torch.from_numpy(rgbn), 200.0).sparse())[0][3:7].numpy()
+            fld = OP._field(cpts, torch.from_numpy(rgbn), 200.0)
+            logits = ov(fld.sparse()).slice(fld).F
+        want = G.pred_center(logits, ee, ee_r=0.02, q=q)
+        assert r.vote_center is not None
+        # the top-8 set can differ where two logits are within fp32 noise of each other: the centres then differ by
+        # at most the size of the crop / 8; with equal sets they agree to float rounding
+        assert np.linalg.norm(r.vote_center - want) < 1e-4, (r.vote_center, want)
+        seen += 1
+    assert seen >= 2

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--prefetch", default="none", choices=["none", "near", "bulk"], help="L2 prefetch scheme")
     ap.add_argument("--sb", type=int, default=0, help="B-ring stages override (flags bits 8-10; 0 = library default)")
     ap.add_argument("--rounds", type=int, default=5, help="--sweep: interleaved timing rounds per variant")
+    ap.add_argument("--lib-b", default=None,
+                    help="--sweep: a second build of libb2me.so; every variant is also timed through it (suffix @B): "
+                         "same-box, interleaved A/B of two kernel versions")
     ap.add_argument("--sweep", action="store_true",
                     help="time every shape under a list of flag variants (operand path, prefetch mode, B-ring depth, "
                          "accumulator layout) on the same map: same-box A/B")
@@ -71,6 +74,16 @@ def main():
     except AttributeError:
         prof_read = None
     res = []
+    lib_a, lib_b = lib, None
+    if a.lib_b:
+        from MinkowskiEngine._lib import SIGNATURES
+        lib_b = C.CDLL(a.lib_b)
+        for name, (rt, at) in SIGNATURES.items():
+            fn = getattr(lib_b, name)
+            fn.restype, fn.argtypes = rt, at
+        variants = [(n, f, lib_a) for n, f in variants] + [(n + "@B", f, lib_b) for n, f in variants]
+    else:
+        variants = [(n, f, lib_a) for n, f in variants]
     for spec in a.shapes.split(","):
         K, cin, cout = [int(x) for x in spec.split(":")]
         g = torch.Generator(device="cuda").manual_seed(1)
@@ -106,11 +119,11 @@ def main():
             # interleaved rounds (the SM clock drifts under the power cap): every variant is timed once per round, the
             # reported time is the median over the rounds
             ref_out = None
-            times = {vn: [] for vn, _ in variants}
+            times = {vn: [] for vn, _, _ in variants}
             same = {}
             for rnd in range(a.rounds):
-                for vname, vflags in variants:
-                    flags = vflags
+                for vname, vflags, vlib in variants:
+                    flags, lib = vflags, vlib
                     if rnd == 0:
                         run()
                         torch.cuda.synchronize()
@@ -124,7 +137,8 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     times[vname].append(e0.elapsed_time(e1) / a.reps)
-            for vname, _ in variants:
+            lib = lib_a
+            for vname, _, _ in variants:
                 ms = float(np.median(times[vname]))
                 print(f"K={K} {cin}->{cout} V={V} [{vname:14s}] median {ms:8.3f} ms (min {min(times[vname]):.3f})  "
                       f"{2.0 * pairs * cin * cout / ms / 1e9:7.0f} TFLOP/s  bit-identical to the first variant: {same[vname]}",

@@ -336,14 +336,14 @@ __device__ __forceinline__ void tc_act_n(float (&v)[N], int mode, float slope) {
     }
 }
 
-// fused head: acc[c] += x[q] * W2[col0 + q][c] for the 16 columns of one accumulator sub-chunk; W2 rows of HCP floats in
+// fused head: acc[c] += x[q] * W2[col0 + q][c] for the 32 columns of one accumulator chunk; W2 rows of HCP floats in
 // shared memory (every lane reads the same address: broadcast)
 template <int HC, int NH>
-__device__ __forceinline__ void tc_head_accumulate(const float (&x)[16], const float* __restrict__ w_rows, int hcp,
+__device__ __forceinline__ void tc_head_accumulate(const float (&x)[32], const float* __restrict__ w_rows, int hcp,
                                                    float (&hacc)[NH]) {
     static_assert(HC <= NH, "head accumulators");
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < 32; ++q) {
         float w[(HC + 3) / 4 * 4];
 #pragma unroll
         for (int g = 0; g < (HC + 3) / 4; ++g) {
@@ -811,7 +811,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     } else {
         // =============================== epilogue ===============================
         // 8 warps: warp e handles TMEM lanes 32 (e & 3) .. (a warp may only touch the lane quarter warp_id % 4) and
-        // the column half e >> 2 of the tile
+        // the column half e >> 2 of the tile. One tcgen05.ld of 32 columns per chunk, waited for at once: splitting a
+        // chunk into two 16-column loads with two register sets (the next load in flight during the arithmetic) was
+        // measured slower (head 3.68 -> 4.44 ms, K = 8 1.77 -> 1.88 ms, same box, interleaved): TMEM reads 64 B/cycle
+        // with 12 cycles of latency, the chunk time is instruction issue, not TMEM latency.
         const int ew = warp - 8;
         const int we = ew & 3, chalf = ew >> 2;
         const int act_mode = tc_act_mode(p.act, p.slope);
@@ -886,30 +889,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
-                // 16-column sub-chunks with two register sets: the tcgen05.ld of sub-chunk i + 1 is in flight while
-                // sub-chunk i is processed (a TMEM read under the MMAs' own TMEM traffic costs about as much as the
-                // arithmetic on it); head mode: n_tile % 64 == 0, every 32-column chunk is two full sub-chunks
-                const int n_sub = 2 * n_my;
-                auto sub_col = [&](int si) -> int { return chunk_col(si >> 1) + 16 * (si & 1); };
-                uint32_t ra[16], rb[16];
-                if (n_sub > 0) tmem_ld_x16(tmem_col(sub_col(0)), ra);
-                for (int si = 0; si < n_sub; ++si) {
-                    const int cb = sub_col(si);
+                for (int ci = 0; ci < n_my; ++ci) {
+                    const int cb = chunk_col(ci);
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem_col(cb), r);  // head mode: n_tile % 64 == 0, every chunk is 32 columns wide
                     tmem_ld_wait();
-                    uint32_t r[16];
-                    if (si & 1) {
+                    release_after(ci);
+                    float x[32];
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) r[q] = rb[q];
-                        if (si + 1 < n_sub) tmem_ld_x16(tmem_col(sub_col(si + 1)), ra);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) r[q] = ra[q];
-                        if (si + 1 < n_sub) tmem_ld_x16(tmem_col(sub_col(si + 1)), rb);
-                    }
-                    if (si == n_sub - 1) release_after(n_my - 1);
-                    float x[16];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
+                    for (int q4 = 0; q4 < 8; ++q4) {
                         const int col = n0 + cb + q4 * 4;
                         const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
                         const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
@@ -922,7 +910,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     // the hidden activation is a bf16 (tf32-rounded fp32) tensor in the unfused data path: same rounding
                     if (ES == 2) {
 #pragma unroll
-                        for (int q = 0; q < 16; q += 2) {
+                        for (int q = 0; q < 32; q += 2) {
                             __nv_bfloat162 h = __floats2bfloat162_rn(x[q], x[q + 1]);
                             const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
                             x[q] = __uint_as_float(u << 16);
@@ -930,7 +918,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) x[q] = round_tf32(x[q]);
+                        for (int q = 0; q < 32; ++q) x[q] = round_tf32(x[q]);
                     }
                     const float* w_rows = head_w_s + (n0 + cb) * p.head_cp;
                     switch (p.head_c) {   // exact FMA count for the class counts of the reference's heads
@@ -1014,13 +1002,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_te_b, 0u);
                 }
-                // 16-column halves with two register sets: while one half of a chunk is scaled / activated / packed, the
-                // tcgen05.ld of the next half (or of the next chunk's first half) is in flight
-                uint32_t ra[16], rb[16];
-                if (n_my > 0) tmem_ld_x16(tmem_col(chunk_col(0)), ra);
                 for (int ci = 0; ci < n_my; ++ci) {
                     const int cb = chunk_col(ci);
-                    const int cw = min(32, p.n_tile - cb);   // 32, or 16 for the last chunk of a tile with n_tile % 32 == 16
+                    const int cw = min(32, p.n_tile - cb);
+                    uint32_t r[32];
+                    if (cw == 32) {
+                        tmem_ld_x32(tmem_col(cb), r);
+                    } else {
+                        tmem_ld_x16(tmem_col(cb), r);
+#pragma unroll
+                        for (int q = 16; q < 32; ++q) r[q] = 0u;
+                    }
                     if (resp) {
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
@@ -1030,58 +1022,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         __syncwarp();
                         if (ci + 1 < n_my) load_res(chunk_col(ci + 1));  // in flight during this chunk's math and stores
                     }
+                    tmem_ld_wait();
+                    release_after(ci);  // this warp's part of the accumulator (region) is read: release it
+                    float v[32];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (half == 1 && cw == 16) break;
-                        tmem_ld_wait();
-                        uint32_t r[16];
-                        if (half == 0) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) r[q] = ra[q];
-                            if (cw == 32) tmem_ld_x16(tmem_col(cb + 16), rb);
-                            else if (ci + 1 < n_my) tmem_ld_x16(tmem_col(chunk_col(ci + 1)), ra);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) r[q] = rb[q];
-                            if (ci + 1 < n_my) tmem_ld_x16(tmem_col(chunk_col(ci + 1)), ra);
-                        }
-                        if (half == 1 || cw == 16) release_after(ci);  // all columns of chunk ci are in registers
-                        float v[16];
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
+                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
+                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                        v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
+                        v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
+                        v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
+                        v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
+                    }
+                    if (resp) {
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4) {
-                            const int col = min(n0 + cb + 16 * half + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
-                            const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
-                            const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
-                            v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
-                            v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
-                            v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
-                            v[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) * sc.w + sh.w;
-                        }
-                        if (resp) {   // this lane's own row of the staged residual block: pieces 2 half, 2 half + 1
-#pragma unroll
-                            for (int q4 = 0; q4 < 2; ++q4) {
-                                const uint4 a4 = ld_shared_v4(own + (uint32_t)(((2 * half + q4) ^ own_sw) << 4));
-                                const uint32_t wv[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
-                                    v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
-                                }
-                            }
-                        }
-                        tc_act_n(v, act_mode, p.slope);
-#pragma unroll
-                        for (int q4 = 0; q4 < 2; ++q4) {
-                            uint32_t wv[4];
+                            const uint4 a = ld_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4));
+                            const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(v[q4 * 8 + 2 * e], v[q4 * 8 + 2 * e + 1]);
-                                wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                                v[q4 * 8 + 2 * e] += __uint_as_float(wv[e] << 16);
+                                v[q4 * 8 + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
                             }
-                            // the lane overwrites the residual pieces it has just read (its own row only)
-                            st_shared_v4(own + (uint32_t)(((2 * half + q4) ^ own_sw) << 4),
-                                         make_uint4(wv[0], wv[1], wv[2], wv[3]));
                         }
+                        __syncwarp();  // every lane has read its residual row before the buffer takes the outputs
+                    }
+                    tc_act_n(v, act_mode, p.slope);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[q4 * 8 + 2 * e], v[q4 * 8 + 2 * e + 1]);
+                            wv[e] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
                     }
                     __syncwarp();
 #pragma unroll

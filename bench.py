@@ -959,13 +959,22 @@ def run_strong(args, rank, world, local):
     class _Rec:   # the fields calibrate() reads (ResultDTO, app/dto.py:37-47)
         pass
 
+    phase = {"predict": 0.0, "assemble": 0.0, "gather": 0.0, "calibrate": 0.0}   # host wall clock per phase, seconds
+
     def job():
+        t_a = time.perf_counter()
         poses = list(eng.predict_stream(batches, depth=max(1, args.depth), fn=one))
+        t_b = time.perf_counter()
         recs = []
         for bi, (B, pose) in enumerate(zip(batches, poses)):
             res = eng.assemble(np.zeros(B["N"], np.uint8), B["offs"], pose)
             recs.append(bdist.pack_records(ids[bi], res))
+        t_c = time.perf_counter()
         allrec = bdist.gather_records(np.concatenate(recs) if recs else np.zeros((0, bdist.RECORD_WIDTH)))
+        t_d = time.perf_counter()
+        phase["predict"] += t_b - t_a
+        phase["assemble"] += t_c - t_b
+        phase["gather"] += t_d - t_c
         cal = None
         if rank == 0:   # InferenceEngine.calibrate over the gathered poses, frames grouped into 5 robot positions
             data = {}
@@ -986,10 +995,13 @@ def run_strong(args, rank, world, local):
                 # the reference's calibrate (app/inference_engine.py:152-194) stacks base_pose with key_points_base_pose
                 # and raises exactly like this when no frame of a position has a key-point pose (random-init weights)
                 cal = None
+        phase["calibrate"] += time.perf_counter() - t_d
         return allrec, cal
 
     for _ in range(max(1, args.warmup)):
         job()
+    for k in phase:
+        phase[k] = 0.0
     sampler = ClockSampler(local)
     sampler.start()
     if world > 1:
@@ -1026,6 +1038,7 @@ def run_strong(args, rank, world, local):
                                              f"the pose records inside the timed region",
                                  "frames_total": F, "batches_in_flight": args.depth},
                       "frames_posed": int(np.nansum(allrec[:, 1])),
+                      "host_phase_ms_rank0": {k: round(v * 1e3 / args.steps, 2) for k, v in phase.items()},
                       "calibration_pose": None if cal is None or cal.pose_camera_link is None
                       else [float(x) for x in cal.pose_camera_link],
                       "per_rank": [{"rank": r, "ms_per_step": float(per[r, 0]), "sm_mhz": float(per[r, 1]),

@@ -461,7 +461,12 @@ class BatchedInferenceEngine:
         import threading
         dev = torch.device("cuda", torch.cuda.current_device())
         main = torch.cuda.current_stream(dev)
-        streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        # the worker streams are kept for the life of the engine: PyTorch's caching allocator pools blocks per stream,
+        # so fresh streams per call would cudaMalloc every activation buffer again on every call
+        pool = self.__dict__.setdefault("_worker_streams", {}).setdefault(dev.index, [])
+        while len(pool) < depth:
+            pool.append(torch.cuda.Stream(dev))
+        streams = pool[:depth]
         q_in, q_out = [queue.Queue() for _ in range(depth)], [queue.Queue() for _ in range(depth)]
 
         def worker(w):

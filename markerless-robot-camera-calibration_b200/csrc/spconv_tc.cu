@@ -165,12 +165,48 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+// try_wait with a suspend-time hint (ns; compiles to NANOSLEEP.SYNCS between two phase checks): the hardware parks the
+// thread until the phase completes or the time is up instead of returning after its short default window. It removes
+// the spin instructions of the waiting roles (ncu: issue slots busy 43 % instead of ~60 % on the K = 1 layers) but
+// changes no layer's time, so the plain form stays the default (-DTC_WAIT_HINT_NS=20000 to enable).
+#ifndef TC_WAIT_HINT_NS
+#define TC_WAIT_HINT_NS 0   // measured (run 10, interleaved two-build medians): no gain on any layer shape, K = 27 -0..5 %
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)TC_WAIT_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
+// predicated 16-byte global store (no branch, no reconvergence point around the store)
+__device__ __forceinline__ void st_global_v4_if(uint4* ptr, const uint4& v, bool on) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+        :
+        : "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)on)
+        : "memory");
+}
+// bounded wait (by time: ~2 s): a protocol bug traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if TC_WAIT_HINT_NS > 0
+    if (mbar_try_wait_hint(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_hint(bar, parity)) {
+        if (clock64() - t0 > (1ll << 32)) __trap();
+    }
+#else
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
+#endif
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -386,10 +422,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
     int32_t* nbr_s0 = reinterpret_cast<int32_t*>(sm + off);
     off += 2 * TC_BM * KT * 4;
     off = (off + 15u) & ~15u;
+    // folded BatchNorm scale / shift, padded by one 32-column chunk of zeros so that the epilogue reads whole chunks
+    // with immediate offsets (no per-access clamp) when the last chunk of a tile is narrower than 32 columns
     float* scale_s = reinterpret_cast<float*>(sm + off);
-    off += p.Cout * 4;
+    off += (p.Cout + 32) * 4;
     float* shift_s = reinterpret_cast<float*>(sm + off);
-    off += p.Cout * 4;
+    off += (p.Cout + 32) * 4;
     off = (off + 15u) & ~15u;
     float* head_w_s = reinterpret_cast<float*>(sm + off);
     off += (uint32_t)(HEAD ? p.Cout * p.head_cp * 4 : 0);
@@ -434,9 +472,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < p.Cout; i += TC_THREADS) {
-        scale_s[i] = p.scale ? p.scale[i] : 1.f;
-        shift_s[i] = p.shift ? p.shift[i] : 0.f;
+    for (int i = tid; i < p.Cout + 32; i += TC_THREADS) {
+        scale_s[i] = i < p.Cout ? (p.scale ? p.scale[i] : 1.f) : 0.f;
+        shift_s[i] = i < p.Cout ? (p.shift ? p.shift[i] : 0.f) : 0.f;
     }
     if (HEAD)
         for (int i = tid; i < p.Cout * p.head_cp; i += TC_THREADS) head_w_s[i] = __ldg(p.head_w + i);
@@ -538,9 +576,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
 #pragma unroll 1
             for (int k = 0; k < KT; ++k) {
                 if (!((kmask >> k) & 1u)) continue;
+                // rows of this offset: index clamped to 0 for an absent neighbour (src-size 0 = zero fill, nothing is
+                // read), presence kept in a bit mask
                 int idx[8];
+                uint32_t have = 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) idx[i] = nbr_s[(rbase + 16 * i) * KT + k];
+                for (int i = 0; i < 8; ++i) {
+                    const int id = nbr_s[(rbase + 16 * i) * KT + k];
+                    have |= (id >= 0 ? 1u : 0u) << i;
+                    idx[i] = max(id, 0);
+                }
                 if ((kmask >> k) == 1u) {  // last offset of this tile: the kernel-map buffer may be refilled
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_nbr_empty + 8 * (it & 1));
@@ -575,20 +620,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 for (int c = 0; c < nchunk; ++c) {
                     PROF(2, mbar_wait(bar_empty + 8 * ist, (uint32_t)iph ^ 1u));
                     PROF_COUNT(7);
+                    // addresses in 16-byte pieces (32-bit: tensors up to 64 GB): row id starts at piece id * rp, this
+                    // thread's piece of chunk cc of that source is cc * 8 + j
                     const uint8_t* src;
-                    int cin, coff;
-                    if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; coff = c * CPC; }
-                    else { src = p.in2; cin = p.Cin2; coff = (c - p.nchunk1) * CPC; }
-                    const int kw = min(CPC, cin - coff);
-                    if (j * EPP < kw && !(p.debug & 1)) {
+                    int cin, cc;
+                    if (c < p.nchunk1) { src = p.in1; cin = p.Cin1; cc = c; }
+                    else { src = p.in2; cin = p.Cin2; cc = c - p.nchunk1; }
+                    const uint32_t rp = (uint32_t)(cin * ES) >> 4;   // pieces per row (Cin % 16 == 0)
+                    const uint32_t pc = (uint32_t)(cc * 8 + j);
+                    if (pc < rp && !(p.debug & 1)) {
                         const uint32_t a_s = base + (uint32_t)ist * TC_A_BYTES;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = rbase + 16 * i;
                             const uint32_t dst = a_s + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-                            const int id = idx[i];
-                            const uint8_t* g = src + (id >= 0 ? ((long long)id * cin + coff + j * EPP) * ES : 0);
-                            cp_async_16(dst, g, id >= 0 ? 16u : 0u);
+                            const uint8_t* g = src + ((unsigned long long)((uint32_t)idx[i] * rp + pc) << 4);
+                            cp_async_16(dst, g, ((have >> i) & 1u) ? 16u : 0u);
                         }
                     }
                     // asynchronous publication: this thread's arrival fires when its copies have landed, so the
@@ -979,17 +1026,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                 int crows[4];  // output rows of the coalesced view
 #pragma unroll
                 for (int m = 0; m < 4; ++m) crows[m] = __shfl_sync(0xffffffffu, row, crow + 8 * m);
-                const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.residual);
-                __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+                const uint4* resp = reinterpret_cast<const uint4*>(p.residual);
+                uint4* outp = reinterpret_cast<uint4*>(p.out);
+                // 16-byte piece index of (row crows[m], column n0 + 8 cq) in the [V_out, Cout] bf16 tensors (32-bit:
+                // the launcher refuses tensors of 64 GB and more); a chunk adds cb / 8
+                uint32_t o16[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    o16[m] = (uint32_t)max(crows[m], 0) * (uint32_t)(p.Cout >> 3) + (uint32_t)((n0 >> 3) + cq);
                 uint4 R[4];
                 auto load_res = [&](int cb) {  // coalesced: 64-byte segment of 8 rows per access
                     const int cw = min(32, p.n_tile - cb);
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         R[m] = make_uint4(0u, 0u, 0u, 0u);
-                        if (crows[m] >= 0 && cq * 8 < cw)
-                            R[m] = __ldg(reinterpret_cast<const uint4*>(resp + (long long)crows[m] * p.Cout + n0 + cb +
-                                                                        cq * 8));
+                        if (crows[m] >= 0 && cq * 8 < cw) R[m] = __ldg(resp + (o16[m] + (uint32_t)(cb >> 3)));
                     }
                 };
                 if (resp && n_my > 0) load_res(chunk_col(0));
@@ -1025,11 +1076,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                     tmem_ld_wait();
                     release_after(ci);  // this warp's part of the accumulator (region) is read: release it
                     float v[32];
+                    const float* scp = scale_s + n0 + cb;  // padded arrays: columns past Cout read zeros
+                    const float* shp = shift_s + n0 + cb;
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
-                        const int col = min(n0 + cb + q4 * 4, p.Cout - 4);  // Cout % 16 == 0: float4-aligned
-                        const float4 sc = *reinterpret_cast<const float4*>(scale_s + col);
-                        const float4 sh = *reinterpret_cast<const float4*>(shift_s + col);
+                        const float4 sc = *reinterpret_cast<const float4*>(scp + q4 * 4);
+                        const float4 sh = *reinterpret_cast<const float4*>(shp + q4 * 4);
                         v[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) * sc.x + sh.x;
                         v[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) * sc.y + sh.y;
                         v[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) * sc.z + sh.z;
@@ -1060,13 +1112,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_spc
                         st_shared_v4(own + (uint32_t)((q4 ^ own_sw) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
                     }
                     __syncwarp();
+                    // all four staged pieces first, then four predicated stores: one shared-memory latency per chunk
+                    // instead of four load -> store round trips through the same registers
+                    uint4 o[4];
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         const int rr = crow + 8 * m;
-                        const uint4 o = ld_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4));
-                        if (crows[m] >= 0 && cq * 8 < cw)
-                            *reinterpret_cast<uint4*>(outp + (long long)crows[m] * p.Cout + n0 + cb + cq * 8) = o;
+                        o[m] = ld_shared_v4(stg + (uint32_t)rr * 64u + (uint32_t)((cq ^ ((rr >> 1) & 3)) << 4));
                     }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        st_global_v4_if(outp + (o16[m] + (uint32_t)(cb >> 3)), o[m], crows[m] >= 0 && cq * 8 < cw);
                     __syncwarp();  // staging is reused by the next chunk
                 }
 #ifdef B2ME_TC_PROFILE
@@ -1269,7 +1325,11 @@ extern "C" int b2me_tc_tile_masks(const int32_t* nbr, const int32_t* perm, int64
 // two accumulators fit the 512 TMEM columns and the epilogue overlaps the next tile's MMAs.
 static int tc_n_tile(int K, int Cout) {
     if (Cout <= 256) return Cout;
+#ifdef TC_K8_SPLIT   // experiment: K = 8 like K = 1 (two 192-column accumulators instead of 256 + 128 rotating)
+    if (K == 27 && Cout <= 384) return Cout;
+#else
     if (K != 1 && Cout <= 384) return Cout;
+#endif
     if (Cout % 256 == 0) return 256;
     if (Cout % 192 == 0) return 192;
     if (Cout % 128 == 0) return 128;
@@ -1444,6 +1504,9 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     if (!nbr && K != 1) return B2ME_EINVAL;
     if (nbr && !tile_masks) return B2ME_EINVAL;
     if (!b2me_tc_supported(K, Cin1, Cin2, Cout)) return B2ME_EUNSUPPORTED;
+    // the gather producers address the sources in 16-byte pieces with 32-bit arithmetic: each source < 64 GB
+    if (((unsigned long long)V_in * (unsigned long long)(Cin1 > Cin2 ? Cin1 : Cin2) * (unsigned)es) >> 36) return B2ME_EUNSUPPORTED;
+    if (((unsigned long long)V_out * (unsigned long long)Cout * 4ull) >> 36) return B2ME_EUNSUPPORTED;  // epilogue: same
     if (!head) {
         if (es == 2 && out_dtype != B2ME_BF16 && out_dtype != B2ME_F32) return B2ME_EINVAL;
         if (es == 4 && out_dtype != B2ME_TF32 && out_dtype != B2ME_F32) return B2ME_EINVAL;
@@ -1502,7 +1565,7 @@ static int tc_run(const void* in1, int Cin1, const void* in2, int Cin2, int64_t 
     if (pairs * p.n_ntiles > 0x7fffffff) return B2ME_EUNSUPPORTED;
     p.n_pairs = (int)pairs;
 
-    const size_t fixed = 1024 /*align slack*/ + 2 * (size_t)TC_BM * K * 4 + 16 + (size_t)Cout * 8 + 16 + head_bytes + 16 +
+    const size_t fixed = 1024 /*align slack*/ + 2 * (size_t)TC_BM * K * 4 + 16 + (size_t)(Cout + 32) * 8 + 16 + head_bytes + 16 +
                          (size_t)TC_EPI_WARPS * TC_STAGE_OUT_BYTES + 16 * TC_MAX_STAGES + 32 + 16 + 24 + 16;
     // B ring: 3 stages of weights (L2-resident, short latency; A/B override in flags bits 8-10), A ring: as many
     // 16 KB stages of gathered rows (DRAM, long latency) as the rest of shared memory holds

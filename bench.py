@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--stages", action="store_true", help="one extra (untimed) step with synchronised per-stage times")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32", "f32"])
-    ap.add_argument("--tc-path", default="cpasync", choices=["cpasync", "tma"], help="operand path of k_spconv_tc")
+    ap.add_argument("--tc-path", default="tma", choices=["cpasync", "tma"], help="operand path of k_spconv_tc")
     ap.add_argument("--no-rot128", action="store_true", help="A/B: single 384-column accumulator (round-1 layout)")
     ap.add_argument("--no-fuse-head", action="store_true", help="A/B: two-launch head (hidden activation in HBM)")
     ap.add_argument("--kp-backbone", default="minkunet", choices=["minkunet", "pointnet2"],

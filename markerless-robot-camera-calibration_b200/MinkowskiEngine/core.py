@@ -53,7 +53,11 @@ class _State:
     compute_dtype = torch.float32
     # "bf16" activations on tcgen05 | "tf32": fp32 activations holding tf32 values on tcgen05 kind::tf32 | "f32": SIMT
     compute_mode = "f32"
-    tc_flags = 0  # B2ME_TC_FLAG_* passed to every tcgen05 launch (operand path, accumulator layout)
+    # B2ME_TC_FLAG_* passed to every tcgen05 launch (operand path, accumulator layout). Default operand path: TMA
+    # (tile::gather4 rows + 2-D weight boxes) - interleaved A/B medians of round 2 (profiles/r02_ab_medians.md): 3-9 %
+    # faster than the cp.async path on the K = 27 384-channel layers, 10-14 % on K = 1 416->384, 22-26 % on the narrow
+    # (32 / 128 channel) layers, never slower; bit-identical results, both paths under the same parity tests
+    tc_flags = _lib.TC_FLAG_TMA
     fuse_head = True  # MinkowskiLinear(.., hidden) -> act -> MinkowskiLinear(hidden, C <= 16) as ONE launch
     launches = 0  # kernels launched through libb2me since the last reset (bench.py reads this)
     lock = threading.Lock()  # several host threads may drive the library (one stream each, pipeline.predict_stream)
@@ -87,8 +91,8 @@ def get_compute_mode():
 
 
 def set_tc_operand_path(path):
-    """how the tcgen05 convolution fetches its operands: "cpasync" (default: 16-byte cp.async gathers + cp.async.bulk
-    weights) or "tma" (cp.async.bulk.tensor tile::gather4 rows + 2-D weight boxes). Bit-identical results."""
+    """how the tcgen05 convolution fetches its operands: "tma" (default: cp.async.bulk.tensor tile::gather4 rows + 2-D
+    weight boxes) or "cpasync" (16-byte cp.async gathers + cp.async.bulk weights). Bit-identical results."""
     if path not in ("cpasync", "tma"):
         raise ValueError('operand path must be "cpasync" or "tma"')
     _State.tc_flags = (_State.tc_flags & ~_lib.TC_FLAG_TMA) | (_lib.TC_FLAG_TMA if path == "tma" else 0)

@@ -306,9 +306,9 @@ def test_fused_head_matches_two_launch_path(V, C2, mode, path):
 def test_tc_operand_path_switch_is_an_api():
     """ME.set_tc_operand_path selects the operand path of every following convolution (no environment variable)."""
     import MinkowskiEngine as ME
+    assert ME.get_tc_operand_path() == "tma"       # the default (faster in the round-2 A/B, profiles/r02_ab_medians.md)
+    ME.set_tc_operand_path("cpasync")
     assert ME.get_tc_operand_path() == "cpasync"
     ME.set_tc_operand_path("tma")
-    assert ME.get_tc_operand_path() == "tma"
-    ME.set_tc_operand_path("cpasync")
     with pytest.raises(ValueError):
         ME.set_tc_operand_path("ldg")

@@ -143,6 +143,28 @@ def test_lazy_fusion_launch_count(nets):
             ME.set_compute_dtype(torch.float32)
 
 
+def test_operand_paths_bit_identical_at_model_level(nets):
+    """the whole segmentation forward through the TMA operand path (default) and the cp.async path: same bits, in both
+    tensor-core modes (each output row is one fp32 accumulation in a fixed (offset, chunk) order on either path)."""
+    ME, _, cnet = nets
+    pts, rgb = _frame(seed=21)
+    co_ = OME.utils.batched_coordinates([pts * 100.0], dtype=torch.float32)
+    for mode in ("bf16", "tf32"):
+        ME.set_compute_dtype(mode)
+        try:
+            outs = {}
+            for path in ("tma", "cpasync"):
+                ME.set_tc_operand_path(path)
+                assert ME.get_tc_operand_path() == path
+                x = ME.TensorField(features=rgb, coordinates=co_, device="cuda").sparse()
+                with torch.no_grad():
+                    outs[path] = cnet(x).F.clone()
+            assert torch.equal(outs["tma"], outs["cpasync"]), (mode, float((outs["tma"] - outs["cpasync"]).abs().max()))
+        finally:
+            ME.set_tc_operand_path("tma")
+            ME.set_compute_dtype(torch.float32)
+
+
 def test_robotnet_full_unet_global_max_pool_parity(nets):
     """model/robotnet.py (full UNet -> BN+ReLU -> MinkowskiGlobalMaxPooling -> MLP)."""
     ME, _, _ = nets

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--level", type=int, default=1, help="tensor stride of the map (1 or 2)")
     ap.add_argument("--out", default=None)
-    ap.add_argument("--path", default="cpasync", choices=["cpasync", "tma"], help="operand path (B2ME_TC_FLAG_TMA)")
+    ap.add_argument("--path", default="tma", choices=["cpasync", "tma"], help="operand path (B2ME_TC_FLAG_TMA)")
     ap.add_argument("--no-rot128", action="store_true", help="384-column tiles: single accumulator (round-1 layout)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--prefetch", default="none", choices=["none", "near", "bulk"], help="L2 prefetch scheme")
@@ -50,8 +50,10 @@ def main():
              | ((a.sb & 7) << 8))
     variants = [("default", flags)]
     if a.sweep:
-        variants = [("default", 0), ("pf_near", TC_FLAG_PF_NEAR), ("sb2", 2 << 8), ("sb4", 4 << 8), ("tma", TC_FLAG_TMA),
-                    ("no_rot128", TC_FLAG_NO_ROT128)]
+        # "default" = the package default (TMA operand path, rot128 accumulators, no L2 prefetch)
+        T = TC_FLAG_TMA
+        variants = [("default", T), ("cpasync", 0), ("tma_no_rot128", T | TC_FLAG_NO_ROT128), ("tma_sb2", T | (2 << 8)),
+                    ("tma_sb4", T | (4 << 8)), ("cpasync_pf_near", TC_FLAG_PF_NEAR)]
     adt = torch.float32 if a.dtype == "tf32" else torch.bfloat16
     from b200calib.synthetic import make_frame
     frames = [make_frame(13000 + i) for i in range(a.frames)]

@@ -52,9 +52,10 @@
 //                 nbr_full (2 prefetch warps)                        nbr_empty    (4 producer warps)
 //                 tmem_full[2] (commit) / tmem_empty[3] (8 epilogue warps of each CTA, on the leader)
 //
-//   B2ME_TC_FLAG_TMA  operands through the TMA unit instead: tile::gather4 copies of the gathered rows (absent
-//                 neighbour = row -1 = out of bounds = zeros) and 2-D boxes of the packed weights, cta_group::2 with
-//                 the LEADER's stage barrier as completion target - no relay, no proxy fence; same speed
+//   B2ME_TC_FLAG_TMA  (what the Python package passes by default) operands through the TMA unit instead: tile::gather4
+//                 copies of the gathered rows (absent neighbour = row -1 = out of bounds = zeros) and 2-D boxes of the
+//                 packed weights, cta_group::2 with the LEADER's stage barrier as completion target - no relay, no
+//                 proxy fence; 3-26 % faster per layer than the cp.async path in round 2 (profiles/r02_ab_medians.md)
 //
 // The two sources (in1 | in2) implement ME.cat without materialising the concatenation.
 #include "common.cuh"

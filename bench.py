@@ -56,7 +56,7 @@ def parse():
                     help="batches in flight of the timed loops (BatchedInferenceEngine.predict_stream: one CUDA stream + "
                          "host thread per batch). Default 1: the convolutions are persistent whole-GPU kernels, so a second "
                          "stream only queues its small kernels behind them (measured: depth 2 = 98 vs 136 frames/s)")
-    ap.add_argument("--crop", default="gt", choices=["gt", "pred", "both"],
+    ap.add_argument("--crop", default="both", choices=["gt", "pred", "both"],
                     help="EE crop of the timed steps: ground-truth labels (stable workload), predicted labels, or both "
                          "(the predicted-crop pass is reported as `pred_crop`)")
     ap.add_argument("--strong-frames", type=int, default=0,

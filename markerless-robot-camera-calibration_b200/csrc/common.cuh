@@ -51,11 +51,22 @@ __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
     return k;
 }
 
+// Home slot of a key. The eight voxels of a 2x2x2 group (lowest bit of x, y, z) share one 128-byte line of the table
+// (8 slots x 16 bytes): the group is hashed, the three low bits pick the slot inside the line. Depth-image points arrive
+// in scan order, so consecutive points and the 27 neighbours of a voxel fall into few lines instead of one random
+// 32-byte sector each. Coordinates that are multiples of a tensor stride >= 2 all start at slot 0 of their line and
+// probe inside it (same line, no extra DRAM access); linear probing keeps the table exact whatever the layout.
+__device__ __forceinline__ unsigned long long hash_slot(unsigned long long key, unsigned long long mask) {
+    const unsigned long long low3 = (key & 1ull) | (((key >> 18) & 1ull) << 1) | (((key >> 36) & 1ull) << 2);
+    const unsigned long long group = key & ~((1ull << 36) | (1ull << 18) | 1ull);
+    return ((hash_key(group) & mask) & ~7ull) | low3;
+}
+
 // read-only probe of a finished table: returns val or 0xFFFFFFFF
 __device__ __forceinline__ unsigned int table_lookup(const HashSlot* __restrict__ tab,
                                                      unsigned long long mask,
                                                      unsigned long long key) {
-    unsigned long long s = hash_key(key) & mask;
+    unsigned long long s = hash_slot(key, mask);
     while (true) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(tab + s));
         const unsigned long long k = ((unsigned long long)v.y << 32) | v.x;

@@ -153,7 +153,7 @@ __global__ void k_hash_insert(const int4* __restrict__ q, int64_t n, HashSlot* _
         return;
     }
     const unsigned long long key = pack_key(c.x, c.y, c.z, c.w);
-    unsigned long long s = hash_key(key) & mask;
+    unsigned long long s = hash_slot(key, mask);
     while (true) {
         unsigned long long prev = tab[s].key;  // cheap pre-read: most probes hit an owned slot
         if (prev != key) {
@@ -434,7 +434,7 @@ extern "C" int b2me_kernel_map_k3(const int32_t* coords, int64_t V, int ts, cons
                                   int32_t* nbr, uint32_t* tile_mask, b2me_stream_t stream) {
     if (!coords || !table || !nbr || V < 0 || ts < 1) return B2ME_EINVAL;
     const int64_t slots = (int64_t)(table_bytes / sizeof(HashSlot));
-    if (slots < 2 || (slots & (slots - 1))) return B2ME_EINVAL;
+    if (slots < 8 || (slots & (slots - 1))) return B2ME_EINVAL;  // hash_slot: 8-slot groups
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (V == 0) return B2ME_OK;
     if (tile_mask) cudaMemsetAsync(tile_mask, 0, (size_t)ceil_div64(V, 128) * sizeof(uint32_t), s);
@@ -600,7 +600,7 @@ extern "C" int b2me_kernel_map_k3_blocks(const int32_t* coords, int64_t V, int t
         return B2ME_EINVAL;
     if (ts > (1 << 14)) return B2ME_EINVAL;
     const int64_t slots = (int64_t)(block_table_bytes / sizeof(HashSlot));
-    if (slots < 2 || (slots & (slots - 1))) return B2ME_EINVAL;
+    if (slots < 8 || (slots & (slots - 1))) return B2ME_EINVAL;  // hash_slot: 8-slot groups
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     cudaMemsetAsync(offset_counts, 0, 32 * sizeof(uint32_t), s);
     if (V == 0) return B2ME_OK;

@@ -7,6 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ITEMS = [  # (log, command, note)
+    ("r2_bench15.log", "python bench.py --stages --no-cpu-baseline", "final build (+ 2x2x2-group table lines in K1), 1 GPU, 1432 MHz box"),
     ("r2_bench13.log", "python bench.py --stages --conv-table ...", "default run, final build (TMA operand path), 1 GPU"),
     ("r2_bench13_again.log", "python bench.py --no-cpu-baseline", "same build, same box, later in the call"),
     ("r2_bench13_cpasync.log", "python bench.py --tc-path cpasync --no-cpu-baseline", "same box: cp.async operand path"),

@@ -145,6 +145,9 @@ def dram(out_md, out_json, d, n):
 def main():
     d, n = sys.argv[1], sys.argv[2]
     p = lambda f: os.path.join(HERE, f)
+    if len(sys.argv) > 3 and sys.argv[3] == "misc":   # only the coordinate-kernel table, from a later run
+        misc(p("r02_ncu_coords_kernels.md"), d, n)
+        return
     with open(p("r02_launches_step32.md"), "w") as fp:
         fp.write("# Launch list of ONE warm 32-frame step (round 2, run %s)\n\n`ncu --profile-from-start off --metrics "
                  "gpu__time_duration.sum --clock-control none --csv python bench.py --frames 32 --steps 1 --warmup 1 "
@@ -153,7 +156,7 @@ def main():
         fp.write(subprocess.run([sys.executable, p("summarize_launches.py"), os.path.join(d, f"r2_launches{n}.csv")],
                                 capture_output=True, text=True).stdout)
     tc(p("r02_ncu_k_spconv_tc.md"), d, n)
-    misc(p("r02_ncu_coords_kernels.md"), d, n)
+    misc(p("r02_ncu_coords_kernels_run%s.md" % n), d, n)
     dram(p("r02_k_spconv_tc_dram_traffic.md"), p("r02_k_spconv_tc_dram_traffic.json"), d, n)
 
 

@@ -379,15 +379,30 @@ __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const 
     best = R2;  // strict '<' below: only neighbours inside the radius qualify
     best_j = 0x7FFFFFFF;
     best_s = -1;
+    // fp32 pre-filter in front of the exact fp64 test (which alone decides, so the result is the fp64 result): a
+    // candidate whose fp32 squared distance exceeds best + `slack` cannot win. slack bounds the fp32 error for every
+    // candidate within sqrt(best) <= sqrt(R2) of the query: rounding the query to fp32 and the subtraction cost at most
+    // e = 3 * 2^-23 (|p|_inf + 2 r) in the coordinates, the squared distance then moves by <= 2 r e + e^2 + 2^-22 d2;
+    // four times that bound is used. Most candidates are rejected after 3 FADD + 3 FFMA instead of 3 fp32->fp64
+    // conversions + 6 fp64 operations.
+    const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
+    const float rmax = sqrtf((float)R2);
+    const float pinf = fmaxf(fabsf(pxf), fmaxf(fabsf(pyf), fabsf(pzf)));
+    const float e32 = 3.6e-7f * (pinf + 2.f * rmax);
+    const float slack = 4.f * (2.f * rmax * e32 + e32 * e32 + 2.4e-7f * (float)R2);
+    float thr = __double2float_ru(best) + slack;
     auto consider = [&](int s) {
         float4 q;
         if (kSmemTargets) q = tg[s];
         else q = __ldg(tg + s);
+        const float fx = pxf - q.x, fy = pyf - q.y, fz = pzf - q.z;
+        if (fmaf(fx, fx, fmaf(fy, fy, fz * fz)) > thr) return;
         const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
         const double d2 = dx * dx + dy * dy + dz * dz;
         const int j = __float_as_int(q.w);
         if (d2 < best || (d2 == best && j < best_j && best_j != 0x7FFFFFFF)) {
             best = d2; best_j = j; best_s = s; bx = q.x; by = q.y; bz = q.z;
+            thr = __double2float_ru(best) + slack;
         }
     };
     if (seed >= 0) consider(seed);

@@ -391,12 +391,12 @@ __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const 
     const float e32 = 3.6e-7f * (pinf + 2.f * rmax);
     const float slack = 4.f * (2.f * rmax * e32 + e32 * e32 + 2.4e-7f * (float)R2);
     float thr = __double2float_ru(best) + slack;
-    auto consider = [&](int s) {
-        float4 q;
-        if (kSmemTargets) q = tg[s];
-        else q = __ldg(tg + s);
+    auto load = [&](int s) -> float4 { return kSmemTargets ? tg[s] : __ldg(tg + s); };
+    auto d2f = [&](const float4& q) -> float {
         const float fx = pxf - q.x, fy = pyf - q.y, fz = pzf - q.z;
-        if (fmaf(fx, fx, fmaf(fy, fy, fz * fz)) > thr) return;
+        return fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+    };
+    auto exact = [&](int s, const float4& q) {   // the deciding test, fp64 like Open3D's KD-tree distances
         const double dx = px - (double)q.x, dy = py - (double)q.y, dz = pz - (double)q.z;
         const double d2 = dx * dx + dy * dy + dz * dz;
         const int j = __float_as_int(q.w);
@@ -404,6 +404,27 @@ __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const 
             best = d2; best_j = j; best_s = s; bx = q.x; by = q.y; bz = q.z;
             thr = __double2float_ru(best) + slack;
         }
+    };
+    auto consider = [&](int s) {
+        const float4 q = load(s);
+        if (d2f(q) <= thr) exact(s, q);
+    };
+    // a run of candidates, four at a time: the four loads and fp32 distances are independent (the search is bound by
+    // the latency of load -> distance -> compare chains, not by issue slots), one branch rejects all four in the
+    // common case; survivors take the exact test in index order, so the result equals the one-by-one scan (thr only
+    // shrinks: testing against the value from before the group is conservative)
+    auto consider_run = [&](int s0, int s1) {
+        int s = s0;
+        for (; s + 4 <= s1; s += 4) {
+            const float4 q0 = load(s), q1 = load(s + 1), q2 = load(s + 2), q3 = load(s + 3);
+            const float e0 = d2f(q0), e1 = d2f(q1), e2 = d2f(q2), e3 = d2f(q3);
+            if (fminf(fminf(e0, e1), fminf(e2, e3)) > thr) continue;
+            if (e0 <= thr) exact(s, q0);
+            if (e1 <= thr) exact(s + 1, q1);
+            if (e2 <= thr) exact(s + 2, q2);
+            if (e3 <= thr) exact(s + 3, q3);
+        }
+        for (; s < s1; ++s) consider(s);
     };
     if (seed >= 0) consider(seed);
     const int cy = icp_cell_coord(py, g.origin[1], g.inv_h, g.dims[1]);
@@ -431,7 +452,7 @@ __device__ __forceinline__ void icp_search(const float4* __restrict__ tg, const 
             if (x0 > x1) continue;
             const int row = (z * g.dims[1] + y) * g.dims[0];
             const int s0 = cs[row + x0], s1 = cs[row + x1 + 1];
-            for (int s = s0; s < s1; ++s) consider(s);
+            consider_run(s0, s1);
         }
     }
 }

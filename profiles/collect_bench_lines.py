@@ -7,6 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ITEMS = [  # (log, command, note)
+    ("r2_bench17.log", "python bench.py --stages --no-cpu-baseline", "final build, 1 GPU, 1413 MHz box"),
     ("r2_bench16.log", "python bench.py --stages --no-cpu-baseline", "final build (+ ICP pre-filter), 1 GPU, 1342 MHz box"),
     ("r2_bench15.log", "python bench.py --stages --no-cpu-baseline", "final build (+ 2x2x2-group table lines in K1), 1 GPU, 1432 MHz box"),
     ("r2_bench13.log", "python bench.py --stages --conv-table ...", "default run, final build (TMA operand path), 1 GPU"),
@@ -16,7 +17,8 @@ ITEMS = [  # (log, command, note)
     ("r2_bench11.log", "python bench.py --stages --crop both ...", "run 11 (cp.async path default), other box; carries `pred_crop`"),
     ("r2_bench10_tf32.log", "python bench.py --dtype tf32 --steps 5", "tf32 tensor-core mode"),
     ("r2_bench8_vote.log", "python bench.py --vote --no-cpu-baseline --stages --steps 4", "with the vote stage"),
-    ("r2_icp1k16.log", "python bench.py --config icp1k", "BASELINE configs[3], final build (fp32 pre-filter in the exact NN search)"),
+    ("r2_icp1k17.log", "python bench.py --config icp1k", "BASELINE configs[3], final build (fp32 pre-filter + four candidates per step in the exact NN search)"),
+    ("r2_icp1k16.log", "python bench.py --config icp1k", "BASELINE configs[3], fp32 pre-filter only"),
     ("r2_icp1k10.log", "python bench.py --config icp1k", "BASELINE configs[3], before the pre-filter"),
     ("r2_sweep7.log", "python bench.py --config sweep", "BASELINE configs[4], 1 GPU, CPU port timed beside every row"),
     ("r2_sweep_8gpu.log", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config sweep --steps 3 --warmup 2 --no-cpu-baseline", "configs[4] at 8 GPUs"),

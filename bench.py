@@ -572,6 +572,10 @@ def run_b200(args, rank, world, local):
             c = dict(recs_census[i])
             ms = [recs_ev[j][0].elapsed_time(recs_ev[j][1]) for j in range(i, len(recs_ev), per_step)]
             c["ms"] = float(np.mean(ms))
+            # time between the end of the previous convolution launch and the start of this one (same stream): the
+            # coordinate kernels at a level change, the other stages between two networks, or the host falling behind
+            gaps = [recs_ev[j - 1][1].elapsed_time(recs_ev[j][0]) for j in range(i, len(recs_ev), per_step) if j % per_step]
+            c["gap_before_ms"] = float(np.mean(gaps)) if gaps else 0.0
             c["tflops"] = 2.0 * c["pairs"] * c["Cin"] * c["Cout"] / (c["ms"] * 1e-3) / 1e12
             c["fill"] = c["pairs"] / max(1, c["K"] * c["V_out"])
             if c.get("passes"):

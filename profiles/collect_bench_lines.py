@@ -7,6 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ITEMS = [  # (log, command, note)
+    ("bench_default.log", "python bench.py   (tools/gpu_run.sh, the round-end validation script)", "final commit, default flags, 1 GPU"),
     ("r2_bench17.log", "python bench.py --stages --no-cpu-baseline", "final build, 1 GPU, 1413 MHz box"),
     ("r2_bench16.log", "python bench.py --stages --no-cpu-baseline", "final build (+ ICP pre-filter), 1 GPU, 1342 MHz box"),
     ("r2_bench15.log", "python bench.py --stages --no-cpu-baseline", "final build (+ 2x2x2-group table lines in K1), 1 GPU, 1432 MHz box"),

@@ -51,6 +51,10 @@ const char* b2me_strerror(int code);
 /* ------------------------------------------------------------------------------------------------
  * Coordinate hashing (K1-K3).  A "table" is an open-addressing hash of 16-byte slots
  * {uint64 key, uint32 val, pad}; key packs (batch:10 | x:18 | y:18 | z:18, biased), val = voxel row.
+ * Home slot: the eight voxels of a 2x2x2 group (lowest bit of x, y, z) share one 128-byte line of 8 slots (the group
+ * is hashed, the three low bits pick the slot), linear probing after that; a table has a power-of-two number of slots,
+ * at least 8 (b2me_table_slots returns at least 1024).  The layout is private to the library: tables are only ever
+ * read by the entry points below.
  * ---------------------------------------------------------------------------------------------- */
 
 /* slots needed for n keys (power of two >= 2n) and the byte size of such a table */

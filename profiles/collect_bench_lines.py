@@ -16,7 +16,8 @@ ITEMS = [  # (log, command, note)
     ("r2_bench13_cpasync.log", "python bench.py --tc-path cpasync --no-cpu-baseline", "same box: cp.async operand path"),
     ("r2_bench13_depth2.log", "python bench.py --depth 2 --no-cpu-baseline", "same box: two batches in flight"),
     ("r2_bench11.log", "python bench.py --stages --crop both ...", "run 11 (cp.async path default), other box; carries `pred_crop`"),
-    ("r2_bench10_tf32.log", "python bench.py --dtype tf32 --steps 5", "tf32 tensor-core mode"),
+    ("r2_bench26_tf32.log", "python bench.py --dtype tf32 --steps 5 --no-cpu-baseline", "tf32 tensor-core mode, final build"),
+    ("r2_bench10_tf32.log", "python bench.py --dtype tf32 --steps 5", "tf32 tensor-core mode, run 10 (cp.async path)"),
     ("r2_bench8_vote.log", "python bench.py --vote --no-cpu-baseline --stages --steps 4", "with the vote stage"),
     ("r2_icp1k17.log", "python bench.py --config icp1k", "BASELINE configs[3], final build (fp32 pre-filter + four candidates per step in the exact NN search)"),
     ("r2_icp1k16.log", "python bench.py --config icp1k", "BASELINE configs[3], fp32 pre-filter only"),

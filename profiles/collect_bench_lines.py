@@ -22,7 +22,8 @@ ITEMS = [  # (log, command, note)
     ("r2_icp1k17.log", "python bench.py --config icp1k", "BASELINE configs[3], final build (fp32 pre-filter + four candidates per step in the exact NN search)"),
     ("r2_icp1k16.log", "python bench.py --config icp1k", "BASELINE configs[3], fp32 pre-filter only"),
     ("r2_icp1k10.log", "python bench.py --config icp1k", "BASELINE configs[3], before the pre-filter"),
-    ("r2_sweep7.log", "python bench.py --config sweep", "BASELINE configs[4], 1 GPU, CPU port timed beside every row"),
+    ("r2_sweep27.log", "python bench.py --config sweep --steps 3 --warmup 2 --no-cpu-baseline", "BASELINE configs[4], 1 GPU, final build"),
+    ("r2_sweep7.log", "python bench.py --config sweep", "BASELINE configs[4], 1 GPU, run 7: CPU port timed beside every row (GPU rows of this run carry the allocator artefact fixed later)"),
     ("r2_sweep_8gpu.log", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config sweep --steps 3 --warmup 2 --no-cpu-baseline", "configs[4] at 8 GPUs"),
     ("r2_bench_8gpu.log", "torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 10 --warmup 3", "weak scaling, 32 frames per GPU"),
     ("r2_strong256_1gpu.log", "python bench.py --strong-frames 256 --steps 2 --warmup 1", "strong scaling reference: 256 uneven frames on 1 GPU (same 8-GPU box)"),

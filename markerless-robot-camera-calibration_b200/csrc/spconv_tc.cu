@@ -4,8 +4,8 @@
 // list (256-row tile pair x n-tile; the n-tiles of one tile pair run back to back on the same cluster) round-robin;
 // each CTA gathers the A rows of its own 128-row tile and loads HALF of every weight tile, the leader CTA issues
 // M = 256 MMAs that read both CTAs' shared memory, and each CTA's TMEM holds the accumulator of its own 128 rows.
-// Halving the per-SM weight traffic is what lets the stage ring be deep enough (4 x 40 KB at n_tile = 384) to cover
-// the DRAM latency of the gathered rows.
+// Halving the per-SM weight traffic leaves shared memory for a deep ring of gathered rows: at n_tile = 384 seven
+// 16 KB A stages (random rows from DRAM: long, variable latency) beside three 24 KB B stages (weights from L2).
 //
 //   operand types ES = 2: bf16 x bf16 (kind::f16), 64 channels per 128-byte chunk, K = 16 per MMA
 //                 ES = 4: tf32 x tf32 (kind::tf32) on fp32 rows, 32 channels per 128-byte chunk, K = 8 per MMA; the
@@ -30,7 +30,8 @@
 //                 activation never does). model/robotnet_segmentation.py:43-49.
 //
 //   warps  0-3    gather producers (stage ring runs on across tiles, so the next tile's rows are in flight while
-//                 the tensor pipe finishes the current one); prefetch.global.L2 of the next offset's rows
+//                 the tensor pipe finishes the current one); optional L2 prefetch of the next offset's rows (off by
+//                 default: the deep A ring already covers the latency, measured)
 //          4      TMEM alloc + MMA issuer (leader) / stage-full relay to the leader's barrier (peer). The issue
 //                 loop is warp-uniform: shfl-broadcast warp index / tile masks / TMEM base, one elect.sync branch
 //                 per item, descriptors as 32-bit low words -> UTCHMMA operands live in uniform registers
